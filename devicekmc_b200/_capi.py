@@ -1,0 +1,115 @@
+"""ctypes binding of include/dkmc.h (libdkmc_b200.so).
+
+There is no CPU fallback: importing the package works without a GPU (so host-side logic can be
+tested), but every compute entry point raises if the library is missing or no device exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libdkmc_b200.so")
+
+DKMC_OK = 0
+DKMC_ERR_CUDA = 1
+DKMC_ERR_ARG = 2
+DKMC_ERR_NOT_CONVERGED = 3
+DKMC_ERR_RNG_EXHAUSTED = 4
+DKMC_ERR_NO_DEVICE = 5
+
+
+class DkmcError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"dkmc status {status}: {msg}")
+        self.status = status
+
+
+class Sparsity(C.Structure):
+    _fields_ = [("m", C.c_int), ("nnz", C.c_int), ("left_nnz", C.c_int), ("right_nnz", C.c_int),
+                ("d_row_ptr", C.c_void_p), ("d_col", C.c_void_p),
+                ("d_left_row_ptr", C.c_void_p), ("d_left_col", C.c_void_p),
+                ("d_right_row_ptr", C.c_void_p), ("d_right_col", C.c_void_p)]
+
+
+class SolverOpts(C.Structure):
+    _fields_ = [("rel_tol", C.c_double), ("max_iter", C.c_int), ("refine_rounds", C.c_int),
+                ("check_every", C.c_int)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("refinements", C.c_int), ("rel_residual", C.c_double),
+                ("assemble_ms", C.c_double), ("solve_ms", C.c_double)]
+
+
+class StepInfo(C.Structure):
+    _fields_ = [("n_events", C.c_int), ("n_used", C.c_int), ("n_exact_fallbacks", C.c_int),
+                ("event_time", C.c_double), ("rate_ms", C.c_double), ("loop_ms", C.c_double)]
+
+
+# every symbol include/dkmc.h declares (tests check the .so exports each one)
+EXPORTS = [
+    "dkmc_version", "dkmc_last_error", "dkmc_get_gpu_info", "dkmc_set_gpu", "dkmc_device_count",
+    "dkmc_ctx_create", "dkmc_ctx_destroy", "dkmc_ctx_set_stream", "dkmc_ctx_synchronize",
+    "dkmc_ctx_launch_count", "dkmc_set_layer_energies", "dkmc_neighbor_count", "dkmc_neighbor_fill",
+    "dkmc_initialize_sparsity", "dkmc_free_sparsity", "dkmc_update_charge", "dkmc_default_solver_opts",
+    "dkmc_background_potential_sparse", "dkmc_assemble_K", "dkmc_spmv", "dkmc_solve_cg",
+    "dkmc_poisson_gridless", "dkmc_poisson_gridless_rows", "dkmc_build_event_list",
+    "dkmc_inclusive_scan", "dkmc_select_event", "dkmc_execute_kmc_step", "dkmc_kmc_step_continue",
+    "dkmc_ctx_set_exact_select", "dkmc_last_event_tables",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the CUDA library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m devicekmc_b200.build` "
+                "(devicekmc-b200 has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.dkmc_last_error.restype = C.c_char_p
+        vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        lib.dkmc_ctx_create.argtypes = [C.POINTER(vp)]
+        lib.dkmc_ctx_destroy.argtypes = [vp]
+        lib.dkmc_ctx_set_stream.argtypes = [vp, vp]
+        lib.dkmc_ctx_synchronize.argtypes = [vp]
+        lib.dkmc_ctx_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+        lib.dkmc_ctx_set_exact_select.argtypes = [vp, ci]
+        lib.dkmc_set_layer_energies.argtypes = [vp, ci, vp, vp, vp, vp]
+        lib.dkmc_neighbor_count.argtypes = [vp, ci, vp, vp, vp, vp, ci, cd, C.POINTER(ci)]
+        lib.dkmc_neighbor_fill.argtypes = [vp, ci, vp, vp, vp, vp, ci, cd, ci, vp]
+        lib.dkmc_initialize_sparsity.argtypes = [vp, ci, ci, vp, ci, ci, C.POINTER(Sparsity)]
+        lib.dkmc_free_sparsity.argtypes = [vp, C.POINTER(Sparsity)]
+        lib.dkmc_update_charge.argtypes = [vp, vp, vp, vp, ci, ci, vp, ci]
+        lib.dkmc_default_solver_opts.argtypes = [C.POINTER(SolverOpts)]
+        lib.dkmc_default_solver_opts.restype = None
+        lib.dkmc_background_potential_sparse.argtypes = [vp, C.POINTER(Sparsity), ci, ci, vp, ci, ci, cd, cd, cd,
+                                                         vp, vp, vp, ci, vp, C.POINTER(SolverOpts),
+                                                         C.POINTER(SolveInfo)]
+        lib.dkmc_assemble_K.argtypes = [vp, C.POINTER(Sparsity), ci, ci, ci, cd, cd, cd, vp, vp, vp, ci, vp, vp]
+        lib.dkmc_spmv.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
+        lib.dkmc_solve_cg.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, C.POINTER(SolverOpts), C.POINTER(SolveInfo)]
+        lib.dkmc_poisson_gridless.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.dkmc_poisson_gridless_rows.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp]
+        lib.dkmc_build_event_list.argtypes = [vp, ci, ci, vp, vp, vp, ci] + [vp] * 13
+        lib.dkmc_inclusive_scan.argtypes = [vp, C.c_longlong, vp, vp]
+        lib.dkmc_select_event.argtypes = [vp, C.c_longlong, vp, cd, C.POINTER(C.c_longlong), C.POINTER(cd)]
+        lib.dkmc_execute_kmc_step.argtypes = [vp, ci, ci, vp, vp, vp, ci] + [vp] * 11 + [vp, ci, vp, ci,
+                                                                                       C.POINTER(StepInfo)]
+        lib.dkmc_kmc_step_continue.argtypes = [vp, vp, ci, vp, ci, C.POINTER(StepInfo)]
+        lib.dkmc_last_event_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        lib.dkmc_get_gpu_info.argtypes = [C.c_char_p, ci, ci]
+        lib.dkmc_set_gpu.argtypes = [ci]
+        lib.dkmc_device_count.argtypes = [C.POINTER(ci)]
+        _lib = lib
+    return _lib
+
+
+def check(status: int, allow=()):
+    if status != DKMC_OK and status not in allow:
+        raise DkmcError(status, load().dkmc_last_error().decode(errors="replace"))
+    return status

@@ -1,0 +1,223 @@
+// devicekmc-b200 — shared host/device plumbing for the sm_100a kernels.
+// Context (workspace arena + stream), error handling, launch accounting and the warp/block
+// reduction primitives every stage uses.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "dkmc.h"
+
+namespace dkmc {
+
+constexpr int kWarp = 32;
+constexpr int kMaxLayers = 16;
+constexpr int kNumSlots = 48;
+constexpr int kMaxLevels = 8;
+
+void set_error(const char *fmt, ...);
+
+#define DKMC_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            ::dkmc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                   \
+                              cudaGetErrorString(err__));                                     \
+            return DKMC_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define DKMC_REQUIRE(cond, msg)                                                               \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            ::dkmc::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, msg);        \
+            return DKMC_ERR_ARG;                                                              \
+        }                                                                                     \
+    } while (0)
+
+// Scratch slots: a persistent arena of named device buffers that only ever grow.
+enum Slot : int {
+    S_SCALARS = 0,   // CG scalars + reduction partials + counters
+    S_PARTIALS,
+    S_CG_R, S_CG_P, S_CG_AP, S_CG_Z, S_CG_DINV, S_CG_RES, S_CG_E, S_CG_VAL, S_CG_RHS,
+    S_SPMV_TILES,
+    S_CLASS,         // per-site conductance class byte
+    S_NB_CELL_OF, S_NB_CELL_START, S_NB_CELL_FILL, S_NB_CELL_SITES, S_NB_DEG, S_NB_BOUNDS,
+    S_SP_CNT, S_SCAN_BLOCK,
+    S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
+    S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
+    S_SCAN_TMP, S_SEL_OUT,
+    S_LAST
+};
+static_assert(S_LAST <= kNumSlots, "increase kNumSlots");
+
+struct SpmvTiling {
+    const int *row_ptr = nullptr;  // key
+    int m = 0, nnz = 0;
+    int num_tiles = 0;
+    int *d_tile_row = nullptr;     // [num_tiles+1] first row of each nnz tile
+};
+
+}  // namespace dkmc
+
+struct dkmc_ctx {
+    cudaStream_t stream = nullptr;
+    int dev = 0;
+    int num_sms = 148;
+    long long launches = 0;
+    void *slot_ptr[dkmc::kNumSlots] = {};
+    size_t slot_cap[dkmc::kNumSlots] = {};
+    // rate-table layer energies: [E_gen | E_rec | E_Vdiff | E_Odiff] x kMaxLayers
+    double *d_layerE = nullptr;
+    int n_layers = 0;
+    // neighbour-grid cache between count and fill
+    struct {
+        int N = 0, ncx = 0, ncy = 0, ncz = 0, pbc = 0;
+        double minx = 0, miny = 0, minz = 0, wx = 0, wy = 0, wz = 0;
+        bool valid = false;
+    } grid;
+    dkmc::SpmvTiling tiling;
+    // event loop state for dkmc_kmc_step_continue
+    struct {
+        int N = 0, nn = 0;
+        const int *d_neigh = nullptr;
+        int *d_element = nullptr, *d_charge = nullptr;
+        const double *d_freq = nullptr;
+        int n_levels = 0;
+        long long level_off[dkmc::kMaxLevels + 1] = {};
+        int level_size[dkmc::kMaxLevels + 1] = {};
+        int events_done = 0;
+        bool active = false;
+    } ev;
+    int exact_select = 0;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+};
+
+namespace dkmc {
+
+// returns a device buffer of at least `bytes` for `slot` (contents NOT preserved on growth)
+int ensure_slot(dkmc_ctx *ctx, int slot, size_t bytes, void **out);
+
+template <typename T>
+inline int ensure(dkmc_ctx *ctx, int slot, size_t count, T **out) {
+    void *p = nullptr;
+    int rc = ensure_slot(ctx, slot, count * sizeof(T), &p);
+    *out = static_cast<T *>(p);
+    return rc;
+}
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#define DKMC_LAUNCH(ctx, kernel, grid, block, smem, ...)                                      \
+    do {                                                                                      \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
+        (ctx)->launches++;                                                                    \
+        cudaError_t err__ = cudaPeekAtLastError();                                            \
+        if (err__ != cudaSuccess) {                                                           \
+            ::dkmc::set_error("%s:%d: launch of %s failed: %s", __FILE__, __LINE__, #kernel,  \
+                              cudaGetErrorString(err__));                                     \
+            return DKMC_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------- device primitives
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// inclusive scan across the warp, fixed (deterministic) Hillis-Steele order
+__device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int warp_inclusive_scan_int(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// block-wide sum; result valid in thread 0.  `sh` must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    double r = 0.0;
+    if (w == 0) {
+        r = lane < nw ? sh[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// Deterministic grid-wide sum: every block deposits its partial, the last block to arrive
+// adds the partials in index order and publishes the total.  `counter` must be 0 on entry and
+// is reset to 0 by the last block.  Returns true in thread 0 of the last block only.
+__device__ __forceinline__ bool grid_sum_finish(double block_total, double *partials,
+                                                unsigned int *counter, double *result,
+                                                double *sh) {
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = block_total;
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(partials + i);
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) {
+        *result = acc;
+        *counter = 0u;
+        __threadfence();
+        return true;
+    }
+    return false;
+}
+
+// utils.cpp:100-137 with every operation individually rounded (no FMA contraction), so the
+// `dist < nn_dist` predicate matches the reference's x86-64 build bit for bit.
+__device__ __forceinline__ double site_dist_exact(double x1, double y1, double z1, double x2,
+                                                  double y2, double z2, double ly, double lz,
+                                                  int pbc) {
+    if (pbc == 1) {
+        double dx = __dsub_rn(x1, x2);
+        double fy = __ddiv_rn(__dsub_rn(y1, y2), ly);
+        fy = __dsub_rn(fy, round(fy));
+        double fz = __ddiv_rn(__dsub_rn(z1, z2), lz);
+        fz = __dsub_rn(fz, round(fz));
+        double dy = __dmul_rn(fy, ly), dz = __dmul_rn(fz, lz);
+        return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    }
+    double ax = __dsub_rn(x2, x1), ay = __dsub_rn(y2, y1), az = __dsub_rn(z2, z1);
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
+}
+
+constexpr double kElementaryCharge = 1.60217663e-19;  // Device.h:113
+constexpr double kBoltzmann = 8.617333262e-5;          // KMCProcess.h:35
+
+// utils.h:102 — potential of a gaussian charge distribution, reference operation order
+__device__ __forceinline__ double v_solve_ref(double r_dist, int charge, double sigma, double k) {
+    return (double)charge * erfc(r_dist / (sigma * sqrt(2.0))) * k * kElementaryCharge / r_dist;
+}
+
+}  // namespace dkmc

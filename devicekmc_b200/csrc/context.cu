@@ -1,0 +1,152 @@
+// devicekmc-b200 — context, error text, device selection (C-ABI plumbing).
+// Replaces get_gpu_info / set_gpu (kmc_events.cu:15-32) and the per-call cudaMalloc/cudaFree
+// churn of the reference (potential_solver_gpu.cu:397-493,735-779) with a persistent arena.
+#include "common.cuh"
+
+namespace dkmc {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int ensure_slot(dkmc_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->slot_cap[slot] < bytes) {
+        if (ctx->slot_ptr[slot]) {
+            DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+            DKMC_CUDA(cudaFree(ctx->slot_ptr[slot]));
+            ctx->slot_ptr[slot] = nullptr;
+            ctx->slot_cap[slot] = 0;
+        }
+        size_t cap = bytes + bytes / 8 + 256;
+        DKMC_CUDA(cudaMalloc(&ctx->slot_ptr[slot], cap));
+        ctx->slot_cap[slot] = cap;
+    }
+    *out = ctx->slot_ptr[slot];
+    return DKMC_OK;
+}
+
+}  // namespace dkmc
+
+using namespace dkmc;
+
+extern "C" {
+
+int dkmc_version(void) { return DKMC_VERSION; }
+
+const char *dkmc_last_error(void) { return g_err; }
+
+int dkmc_device_count(int *count) {
+    DKMC_REQUIRE(count != nullptr, "count");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return DKMC_ERR_NO_DEVICE;
+    }
+    return DKMC_OK;
+}
+
+int dkmc_get_gpu_info(char *name, int name_cap, int dev) {
+    DKMC_REQUIRE(name != nullptr && name_cap > 0, "name buffer");
+    cudaDeviceProp prop;
+    DKMC_CUDA(cudaSetDevice(dev));
+    DKMC_CUDA(cudaGetDeviceProperties(&prop, dev));
+    strncpy(name, prop.name, (size_t)name_cap - 1);
+    name[name_cap - 1] = '\0';
+    return DKMC_OK;
+}
+
+int dkmc_set_gpu(int dev) {
+    DKMC_CUDA(cudaSetDevice(dev));
+    return DKMC_OK;
+}
+
+int dkmc_ctx_create(dkmc_ctx **out) {
+    DKMC_REQUIRE(out != nullptr, "ctx out");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        set_error("no CUDA device: the devicekmc-b200 hot path has no CPU fallback");
+        return DKMC_ERR_NO_DEVICE;
+    }
+    dkmc_ctx *ctx = new dkmc_ctx();
+    DKMC_CUDA(cudaGetDevice(&ctx->dev));
+    DKMC_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->dev));
+    DKMC_CUDA(cudaMalloc(&ctx->d_layerE, 4 * kMaxLayers * sizeof(double)));
+    DKMC_CUDA(cudaMemset(ctx->d_layerE, 0, 4 * kMaxLayers * sizeof(double)));
+    DKMC_CUDA(cudaEventCreate(&ctx->ev_a));
+    DKMC_CUDA(cudaEventCreate(&ctx->ev_b));
+    DKMC_CUDA(cudaEventCreate(&ctx->ev_c));
+    *out = ctx;
+    return DKMC_OK;
+}
+
+int dkmc_ctx_destroy(dkmc_ctx *ctx) {
+    if (!ctx) return DKMC_OK;
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < kNumSlots; ++s)
+        if (ctx->slot_ptr[s]) cudaFree(ctx->slot_ptr[s]);
+    if (ctx->tiling.d_tile_row) cudaFree(ctx->tiling.d_tile_row);
+    if (ctx->d_layerE) cudaFree(ctx->d_layerE);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->ev_c) cudaEventDestroy(ctx->ev_c);
+    delete ctx;
+    return DKMC_OK;
+}
+
+int dkmc_ctx_set_stream(dkmc_ctx *ctx, void *cuda_stream) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return DKMC_OK;
+}
+
+int dkmc_ctx_synchronize(dkmc_ctx *ctx) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DKMC_OK;
+}
+
+int dkmc_ctx_launch_count(dkmc_ctx *ctx, long long *count) {
+    DKMC_REQUIRE(ctx != nullptr && count != nullptr, "ctx/count");
+    *count = ctx->launches;
+    return DKMC_OK;
+}
+
+int dkmc_ctx_set_exact_select(dkmc_ctx *ctx, int mode) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    ctx->exact_select = mode;
+    return DKMC_OK;
+}
+
+int dkmc_set_layer_energies(dkmc_ctx *ctx, int n_layers, const double *E_gen, const double *E_rec,
+                            const double *E_Vdiff, const double *E_Odiff) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    DKMC_REQUIRE(n_layers > 0 && n_layers <= kMaxLayers, "n_layers must be in 1..16");
+    double host[4 * kMaxLayers] = {};
+    for (int l = 0; l < n_layers; ++l) {
+        host[0 * kMaxLayers + l] = E_gen[l];
+        host[1 * kMaxLayers + l] = E_rec[l];
+        host[2 * kMaxLayers + l] = E_Vdiff[l];
+        host[3 * kMaxLayers + l] = E_Odiff[l];
+    }
+    DKMC_CUDA(cudaMemcpyAsync(ctx->d_layerE, host, sizeof(host), cudaMemcpyHostToDevice, ctx->stream));
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->n_layers = n_layers;
+    return DKMC_OK;
+}
+
+void dkmc_default_solver_opts(dkmc_solver_opts *o) {
+    if (!o) return;
+    o->rel_tol = 1e-12;
+    o->max_iter = 20000;
+    o->refine_rounds = 2;
+    o->check_every = 32;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// devicekmc-b200 — pairwise (gridless) Coulomb potential of the charged sites.
+//   a6  Device::poisson_gridless + v_solve (CPU semantics)    potential_solver.cpp:412-432, utils.h:102
+//       poisson_gridless_gpu / calculate_pairwise_interaction  potential_solver_gpu.cu:908-978
+// phi_c[i] = sum_{j != i, q_j != 0} q_j * erfc(r_ij / (sigma*sqrt(2))) * k * q_e / r_ij,  r in metres.
+// The reference launches N*ceil(N/512) blocks, one thread per (i,j) pair incl. uncharged j, and
+// combines with a shared-memory tree + atomicAdd(double).  Here: the charged sites are
+// compacted (ascending j = the CPU summation order), tiles of them are staged in shared memory
+// and every thread owns one target site and accumulates in registers — no atomics, FP64-pipe
+// bound, O(N * N_charged).
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace dkmc {
+
+constexpr int kPwThreads = 128;
+constexpr int kPwTile = 256;       // charged sources per shared-memory tile
+constexpr int kCompactBlock = 1024;
+
+struct __align__(32) ChargedSite { double x, y, z, q; };
+
+__global__ void __launch_bounds__(kCompactBlock) charged_count_kernel(int N, const int *__restrict__ charge,
+                                                                    int *__restrict__ block_count) {
+    __shared__ int sh[32];
+    int i = blockIdx.x * kCompactBlock + threadIdx.x;
+    int f = (i < N && charge[i] != 0) ? 1 : 0;
+    unsigned b = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = sh[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) block_count[blockIdx.x] = v;
+    }
+}
+
+// block_incl = inclusive scan of block_count.  Writes the charged sites in ascending site order.
+__global__ void __launch_bounds__(kCompactBlock) charged_scatter_kernel(
+    int N, int nblocks, const int *__restrict__ charge, const double *__restrict__ x,
+    const double *__restrict__ y, const double *__restrict__ z, const int *__restrict__ block_count,
+    const int *__restrict__ block_incl, ChargedSite *__restrict__ src, int *__restrict__ src_idx,
+    int *__restrict__ total) {
+    __shared__ int sh[32];
+    int i = blockIdx.x * kCompactBlock + threadIdx.x;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int q = i < N ? charge[i] : 0;
+    int f = q != 0 ? 1 : 0;
+    unsigned b = __ballot_sync(0xffffffffu, f);
+    int in_warp = __popc(b & ((1u << lane) - 1u));
+    if (lane == 0) sh[w] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = sh[threadIdx.x];
+        int inc = warp_inclusive_scan_int(v, threadIdx.x);
+        sh[threadIdx.x] = inc - v;
+    }
+    __syncthreads();
+    int base = block_incl[blockIdx.x] - block_count[blockIdx.x];
+    if (f) {
+        int pos = base + sh[w] + in_warp;
+        ChargedSite s;
+        s.x = x[i]; s.y = y[i]; s.z = z[i]; s.q = (double)q;
+        src[pos] = s;
+        src_idx[pos] = i;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total = block_incl[nblocks - 1];
+}
+
+__global__ void __launch_bounds__(kPwThreads) pairwise_kernel(
+    int row_begin, int row_end, const double *__restrict__ x, const double *__restrict__ y,
+    const double *__restrict__ z, const int *__restrict__ n_src_ptr, const ChargedSite *__restrict__ src,
+    const int *__restrict__ src_idx, const double *__restrict__ lattice, int pbc,
+    const double *__restrict__ sigma_ptr, const double *__restrict__ k_ptr, double *__restrict__ out) {
+    __shared__ ChargedSite tile[kPwTile];
+    __shared__ int tile_idx[kPwTile];
+    const int i = row_begin + blockIdx.x * kPwThreads + threadIdx.x;
+    const bool valid = i < row_end;
+    const double xi = valid ? x[i] : 0.0, yi = valid ? y[i] : 0.0, zi = valid ? z[i] : 0.0;
+    const int nsrc = *n_src_ptr;
+    const double sigma = *sigma_ptr, kc = *k_ptr;
+    const double ly = lattice[1], lz = lattice[2];
+    const double denom = sigma * sqrt(2.0);
+    double acc = 0.0;
+    for (int t0 = 0; t0 < nsrc; t0 += kPwTile) {
+        const int nt = min(kPwTile, nsrc - t0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nt; t += kPwThreads) {
+            tile[t] = src[t0 + t];
+            tile_idx[t] = src_idx[t0 + t];
+        }
+        __syncthreads();
+        if (valid) {
+            for (int t = 0; t < nt; ++t) {
+                if (tile_idx[t] == i) continue;  // i != j (potential_solver.cpp:422)
+                const ChargedSite s = tile[t];
+                double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
+                if (pbc) {
+                    double fy = dy / ly; fy -= round(fy); dy = fy * ly;
+                    double fz = dz / lz; fz -= round(fz); dz = fz * lz;
+                }
+                double r = 1e-10 * sqrt(dx * dx + dy * dy + dz * dz);
+                acc += s.q * erfc(r / denom) * kc * kElementaryCharge / r;
+            }
+        }
+    }
+    if (valid) out[i] = acc;
+}
+
+}  // namespace dkmc
+
+using namespace dkmc;
+
+extern "C" {
+
+int dkmc_poisson_gridless_rows(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice, const double *d_sigma,
+                               const double *d_k, const double *d_x, const double *d_y, const double *d_z,
+                               const int *d_site_charge, int row_begin, int row_end,
+                               double *d_site_potential_charge) {
+    DKMC_REQUIRE(ctx && d_lattice && d_sigma && d_k && d_x && d_y && d_z && d_site_charge && d_site_potential_charge,
+                 "null pointer");
+    DKMC_REQUIRE(N > 0 && row_begin >= 0 && row_end <= N && row_begin <= row_end, "row range");
+    if (row_begin == row_end) return DKMC_OK;
+    const int nb = ceil_div(N, kCompactBlock);
+    int *counts, *tmp, *src_idx;
+    ChargedSite *src;
+    int rc;
+    // counts | inclusive | total
+    if ((rc = ensure<int>(ctx, S_PW_COUNT, (size_t)2 * nb + 4, &counts))) return rc;
+    if ((rc = ensure<int>(ctx, S_SCAN_BLOCK, (size_t)ceil_div(nb, kScanTile) + 1, &tmp))) return rc;
+    if ((rc = ensure<ChargedSite>(ctx, S_PW_SRC, (size_t)N, &src))) return rc;
+    if ((rc = ensure<int>(ctx, S_PW_FLAGS, (size_t)N, &src_idx))) return rc;
+    int *incl = counts + nb, *total = counts + 2 * nb;
+    DKMC_LAUNCH(ctx, charged_count_kernel, nb, kCompactBlock, 0, N, d_site_charge, counts);
+    if ((rc = inclusive_scan<int>(ctx, counts, nb, incl, tmp))) return rc;
+    DKMC_LAUNCH(ctx, charged_scatter_kernel, nb, kCompactBlock, 0, N, nb, d_site_charge, d_x, d_y, d_z, counts, incl,
+                src, src_idx, total);
+    const int rows = row_end - row_begin;
+    DKMC_LAUNCH(ctx, pairwise_kernel, ceil_div(rows, kPwThreads), kPwThreads, 0, row_begin, row_end, d_x, d_y, d_z,
+                total, src, src_idx, d_lattice, pbc, d_sigma, d_k, d_site_potential_charge);
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DKMC_OK;
+}
+
+int dkmc_poisson_gridless(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice, const double *d_sigma,
+                          const double *d_k, const double *d_x, const double *d_y, const double *d_z,
+                          const int *d_site_charge, double *d_site_potential_charge) {
+    return dkmc_poisson_gridless_rows(ctx, pbc, N, d_lattice, d_sigma, d_k, d_x, d_y, d_z, d_site_charge, 0, N,
+                                      d_site_potential_charge);
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+/* devicekmc-b200 — C-ABI of the B200-native field-and-rate hot path of DeviceKMC.
+ *
+ * Plain C linkage, plain pointers and sizes.  Every `d_*` pointer is DEVICE memory owned by
+ * the caller (the reference keeps them in `GPUBuffers`, gpu_buffers.h:16-55); every other
+ * pointer is host memory.  All functions return a dkmc_status (0 = OK) and never print;
+ * dkmc_last_error() returns the text of the last failure on the calling thread.
+ * Work is issued on the context's stream and is COMPLETE on return unless stated otherwise
+ * (the reference's callers read results right after each call).
+ *
+ * Each entry point names the reference interface it replaces (file:line in
+ * manasakani/DeviceKMC, src/).  The reference-named `extern "C"` shim that forwards the
+ * gpu_solvers.h signatures to these functions is devicekmc_b200/shim/gpu_solvers_shim.cu;
+ * INTEGRATION.md shows how a maintainer links it.
+ */
+#ifndef DKMC_H
+#define DKMC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DKMC_VERSION 100
+
+typedef enum {
+    DKMC_OK = 0,
+    DKMC_ERR_CUDA = 1,          /* a CUDA runtime call or kernel failed */
+    DKMC_ERR_ARG = 2,           /* invalid argument */
+    DKMC_ERR_NOT_CONVERGED = 3, /* CG hit max_iter (solution still written) */
+    DKMC_ERR_RNG_EXHAUSTED = 4, /* event loop consumed all supplied uniforms; call again */
+    DKMC_ERR_NO_DEVICE = 5
+} dkmc_status;
+
+/* ELEMENT / EVENTTYPE values are the reference's 4-byte unscoped enums, utils.h:37-60 */
+enum { DKMC_DEFECT = 0, DKMC_OXYGEN_DEFECT = 1, DKMC_VACANCY = 2, DKMC_O_EL = 3, DKMC_Hf_EL = 4,
+       DKMC_Ni_EL = 5, DKMC_Ti_EL = 6, DKMC_Pt_EL = 7, DKMC_N_EL = 8, DKMC_NULL_ELEMENT = 9 };
+enum { DKMC_VACANCY_GENERATION = 0, DKMC_VACANCY_RECOMBINATION = 1, DKMC_VACANCY_DIFFUSION = 2,
+       DKMC_ION_DIFFUSION = 3, DKMC_NULL_EVENT = 4 };
+
+typedef struct dkmc_ctx dkmc_ctx; /* workspace: stream, scratch arena, cached CSR tiling */
+
+int dkmc_version(void);
+const char *dkmc_last_error(void);
+
+/* get_gpu_info / set_gpu, gpu_solvers.h:113-114 (kmc_events.cu:15-32) */
+int dkmc_get_gpu_info(char *name, int name_cap, int dev);
+int dkmc_set_gpu(int dev);
+int dkmc_device_count(int *count);
+
+/* Workspace bound to the current device.  The reference mallocs/frees scratch inside every
+ * call (potential_solver_gpu.cu:397-493,735-779; kmc_events.cu:163-164,362); here it is a
+ * persistent arena that grows on demand. */
+int dkmc_ctx_create(dkmc_ctx **ctx);
+int dkmc_ctx_destroy(dkmc_ctx *ctx);
+int dkmc_ctx_set_stream(dkmc_ctx *ctx, void *cuda_stream); /* cudaStream_t; default 0 */
+int dkmc_ctx_synchronize(dkmc_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py "gpu_launches") */
+int dkmc_ctx_launch_count(dkmc_ctx *ctx, long long *count);
+
+/* copytoConstMemory, gpu_solvers.h:205 (kmc_events.cu:369-375): per-layer zero-field
+ * activation energies used by the rate table.  n_layers <= 16. */
+int dkmc_set_layer_energies(dkmc_ctx *ctx, int n_layers, const double *E_gen, const double *E_rec,
+                            const double *E_Vdiff, const double *E_Odiff);
+
+/* ---- a1: neighbour graph.  Device::constructSiteNeighborList, Device.cpp:98-136,175-199 and
+ * the padded table Device.cpp:68-80 (rows ascending in j, padded with -1), via a cell list.
+ * `lattice` is a HOST double[3].  count: writes the max degree (Device::max_num_neighbors);
+ * fill: writes d_neigh_idx[N*nn].  fill must follow count on the same positions. */
+int dkmc_neighbor_count(dkmc_ctx *ctx, int N, const double *d_x, const double *d_y, const double *d_z,
+                        const double *lattice, int pbc, double nn_dist, int *max_nn);
+int dkmc_neighbor_fill(dkmc_ctx *ctx, int N, const double *d_x, const double *d_y, const double *d_z,
+                       const double *lattice, int pbc, double nn_dist, int nn, int *d_neigh_idx);
+
+/* ---- a2: CSR structure of K.  initialize_sparsity, gpu_solvers.h:43
+ * (iterative_solvers_gpu.cu:96-109 -> Assemble_K_sparsity :2158-2208).  The arrays are
+ * allocated by the library (as the reference's `int **` out-parameters are) and have the
+ * GPUBuffers meaning: interior block m x m with the diagonal, interior-relative ascending
+ * columns; contact blocks with contact-relative columns.  m = N - NL - NR. */
+typedef struct {
+    int m, nnz, left_nnz, right_nnz;
+    int *d_row_ptr, *d_col;             /* GPUBuffers::Device_row_ptr_d / Device_col_indices_d */
+    int *d_left_row_ptr, *d_left_col;   /* contact_left_row_ptr / contact_left_col_indices */
+    int *d_right_row_ptr, *d_right_col; /* contact_right_row_ptr / contact_right_col_indices */
+} dkmc_sparsity;
+int dkmc_initialize_sparsity(dkmc_ctx *ctx, int N, int nn, const int *d_neigh_idx, int NL, int NR,
+                             dkmc_sparsity *out);
+int dkmc_free_sparsity(dkmc_ctx *ctx, dkmc_sparsity *sp);
+
+/* ---- a3: charge state machine.  update_charge_gpu, gpu_solvers.h:127-130
+ * (CPU semantics potential_solver.cpp:172-217).  Asynchronous like the reference's. */
+int dkmc_update_charge(dkmc_ctx *ctx, const int *d_site_element, int *d_site_charge,
+                       const int *d_neigh_idx, int N, int nn, const int *d_metals, int num_metals);
+
+/* ---- a4 + a5: background potential.  background_potential_gpu_sparse, gpu_solvers.h:139-141
+ * (potential_solver_gpu.cu:696-781; CPU semantics potential_solver.cpp:289-410).
+ * Assembles K on the neighbour graph, solves the interior system with Jacobi-preconditioned
+ * CG warm-started from d_site_potential_boundary, refines with a double-double residual and
+ * writes the Dirichlet contacts (-Vd/2, +Vd/2). */
+typedef struct {
+    double rel_tol;      /* CG stop: ||r||_D^-1 <= rel_tol * ||b||_D^-1   (default 1e-12) */
+    int max_iter;        /* per CG run (default 20000) */
+    int refine_rounds;   /* double-double residual refinements (default 2) */
+    int check_every;     /* iterations between host convergence polls (default 32) */
+} dkmc_solver_opts;
+typedef struct {
+    int iterations;        /* total CG iterations incl. refinement runs */
+    int refinements;       /* refinement rounds executed */
+    double rel_residual;   /* final double-double ||b - A x||_2 / ||b||_2 */
+    double assemble_ms, solve_ms; /* device time of the two phases */
+} dkmc_solve_info;
+void dkmc_default_solver_opts(dkmc_solver_opts *o);
+int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int nn,
+                                     const int *d_neigh_idx, int NL, int NR, double Vd,
+                                     double high_G, double low_G, const int *d_site_element,
+                                     const int *d_site_charge, const int *d_metals, int num_metals,
+                                     double *d_site_potential_boundary,
+                                     const dkmc_solver_opts *opts, dkmc_solve_info *info);
+
+/* building blocks of a4/a5, exported for parity tests and the roofline measurements */
+int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd,
+                    double high_G, double low_G, const int *d_site_element, const int *d_site_charge,
+                    const int *d_metals, int num_metals, double *d_val, double *d_rhs);
+/* y = A x, CSR FP64/int32 (replaces cusparseSpMV, iterative_solvers_gpu.cu:411,428) */
+int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
+              const double *d_val, const double *d_x, double *d_y);
+int dkmc_solve_cg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
+                  const double *d_val, const double *d_rhs, double *d_x,
+                  const dkmc_solver_opts *opts, dkmc_solve_info *info);
+
+/* ---- a6: pairwise Coulomb sum.  poisson_gridless_gpu, gpu_solvers.h:144-147
+ * (potential_solver_gpu.cu:908-978; CPU semantics potential_solver.cpp:412-432, utils.h:102).
+ * d_lattice/d_sigma/d_k are device scalars/arrays exactly as the reference passes them. */
+int dkmc_poisson_gridless(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice,
+                          const double *d_sigma, const double *d_k, const double *d_x,
+                          const double *d_y, const double *d_z, const int *d_site_charge,
+                          double *d_site_potential_charge);
+/* same sum restricted to the target range [row_begin,row_end) (slab-partitioned ranks) */
+int dkmc_poisson_gridless_rows(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice,
+                               const double *d_sigma, const double *d_k, const double *d_x,
+                               const double *d_y, const double *d_z, const int *d_site_charge,
+                               int row_begin, int row_end, double *d_site_potential_charge);
+
+/* ---- a7: rate table.  build_event_list, kmc_events.cu:34-126 with the CPU semantics of
+ * KMCProcess::update_events_and_rates, KMCProcess.cpp:67-164 (vacancy-diffusion barrier from
+ * layer[i]).  d_event_type int32[N*nn], d_event_prob double[N*nn]. */
+int dkmc_build_event_list(dkmc_ctx *ctx, int N, int nn, const int *d_neigh_idx, const int *d_site_layer,
+                          const double *d_lattice, int pbc, const double *d_T_bg, const double *d_freq,
+                          const double *d_sigma, const double *d_k, const double *d_x, const double *d_y,
+                          const double *d_z, const double *d_potential_boundary,
+                          const double *d_potential_charge, const int *d_site_element,
+                          const int *d_site_charge, int *d_event_type, double *d_event_prob);
+
+/* inclusive prefix sum (utils.h:91-99 / thrust::inclusive_scan kmc_events.cu:214), parallel
+ * block-level scan; and upper_bound selection (KMCProcess.cpp:311 / kmc_events.cu:222):
+ * first idx with cum[idx] > u * cum[n-1].  Exported for parity tests and the scan roofline. */
+int dkmc_inclusive_scan(dkmc_ctx *ctx, long long n, const double *d_in, double *d_out);
+int dkmc_select_event(dkmc_ctx *ctx, long long n, const double *d_cum, double u, long long *idx,
+                      double *Psum);
+
+/* ---- a7 + a8: one KMC step.  execute_kmc_step_gpu, gpu_solvers.h:196-201
+ * (kmc_events.cu:146-365; CPU semantics KMCProcess.cpp:282-365).  Builds the rate table, then
+ * runs the residence-time loop entirely on the device: select (prefix sums + search), execute,
+ * zero the conflicting events, draw the residence time — until event_time >= 1/freq.
+ * `uniforms` is the HOST array of the next n_uniforms numbers of the reference's
+ * RandomNumberGenerator stream (random_num.h:4-23), two per executed event; *n_used tells the
+ * caller how far to advance its generator.  Returns DKMC_ERR_RNG_EXHAUSTED if the loop needs
+ * more numbers: call dkmc_kmc_step_continue with the following numbers of the stream.
+ * events_out (host, may be NULL): (table idx, i, j, type) per executed event, up to max_events. */
+typedef struct {
+    int n_events;          /* events executed in this step */
+    int n_used;            /* uniforms consumed */
+    int n_exact_fallbacks; /* selections decided by the exact sequential replay */
+    double event_time;     /* the last residence-time draw (what the reference returns) */
+    double rate_ms, loop_ms;
+} dkmc_step_info;
+int dkmc_execute_kmc_step(dkmc_ctx *ctx, int N, int nn, const int *d_neigh_idx, const int *d_site_layer,
+                          const double *d_lattice, int pbc, const double *d_T_bg, const double *d_freq,
+                          const double *d_sigma, const double *d_k, const double *d_x, const double *d_y,
+                          const double *d_z, const double *d_potential_boundary,
+                          const double *d_potential_charge, int *d_site_element, int *d_site_charge,
+                          const double *uniforms, int n_uniforms, int *events_out, int max_events,
+                          dkmc_step_info *info);
+int dkmc_kmc_step_continue(dkmc_ctx *ctx, const double *uniforms, int n_uniforms, int *events_out,
+                           int max_events, dkmc_step_info *info);
+/* test hook: force every selection through the exact sequential replay (1) or never (0, default) */
+int dkmc_ctx_set_exact_select(dkmc_ctx *ctx, int mode);
+/* device pointers of the last step's event tables (valid until the next step) */
+int dkmc_last_event_tables(dkmc_ctx *ctx, const int **d_event_type, const double **d_event_prob);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DKMC_H */

@@ -1,0 +1,101 @@
+"""Generates the golden fixtures under tests/golden/ from the UNMODIFIED reference CPU build
+(oracle/_ref/libdkmc_ref.so, see oracle/Makefile).  Runs only where /root/reference exists.
+
+    python tests/golden/make_golden.py
+
+Fixtures (config 0 of BASELINE.json: structures/single_devices/test_2.5nm, rnd_seed = 4,
+rnd_seed_kmc = 1, CPU build, 1 process):
+
+  s_step0.npz      state after Device ctor + makeSubstoichiometric + updateCharge + potentials at
+                   Vd = 1.5 V + the rate table (non-zero entries) — every stage of one step
+  s_traj_ramp.npz  the kmc_main.cpp:136-279 loop on the shipped V_switch ramp, first 12 KMC steps:
+                   per step Vd, executed (i, j) pairs, step time, sha256 of site_element/charge
+  s_traj_6V.npz    the same loop at constant Vd = 6 V, 6 KMC steps (many events per step)
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refsim as R  # noqa: E402
+
+REF = "/root/reference/structures/single_devices/test_2.5nm/"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def new_sim():
+    return R.RefSim(REF + "parameters.txt", REF + "reordered_device_2.5.xyz")
+
+
+def step0():
+    s = new_sim()
+    x, y, z = s.positions()
+    nb = s.neigh_idx()
+    el = s.element()
+    s.update_charge()
+    q = s.charge()
+    Vd = 1.5
+    s.background_potential(Vd)
+    s.poisson_gridless()
+    pb, pc = s.potential_boundary(), s.potential_charge()
+    et, ep = s.rate_table()
+    nz = np.nonzero(et != 4)[0]
+    np.savez_compressed(
+        os.path.join(OUT, "s_step0.npz"),
+        N=s.N, nn=s.nn, Vd=Vd, n_contact=s.num_atoms_contact, pbc=s.pbc,
+        params=np.array([s.sigma, s.k, s.T_bg, s.freq, s.nn_dist, s.high_G, s.low_G]), lattice=s.lattice,
+        metals=s.metals, layers=s.layers, site_layer=s.site_layer().astype(np.int8),
+        neigh_sha=sha(nb), degree=(nb >= 0).sum(1).astype(np.int8),
+        element=el.astype(np.int8), charge=q.astype(np.int8),
+        potential_boundary=pb, potential_charge=pc,
+        ev_idx=nz.astype(np.int32), ev_type=et[nz].astype(np.int8), ev_prob=ep[nz],
+        kmc_rng_first16=s.peek_kmc_rng(16))
+    print("step0 written", len(nz), "events")
+
+
+def trajectory(name, schedule, nsteps):
+    """schedule: list of (Vd, t) bias points as in kmc_main.cpp:136-279"""
+    s = new_sim()
+    rec = dict(Vd=[], step_time=[], ev_ptr=[0], ev_ij=[], el_sha=[], q_sha=[], n_charged=[])
+    count = 0
+    for Vd, t in schedule:
+        kmc_time = 0.0
+        while kmc_time < t and count < nsteps:
+            s.update_charge()
+            s.background_potential(Vd)
+            s.poisson_gridless()
+            if count == 0:
+                rec["pb0"], rec["pc0"] = s.potential_boundary(), s.potential_charge()
+            rec["n_charged"].append(int(np.count_nonzero(s.charge())))
+            dt, ev = s.kmc_step()
+            kmc_time += dt
+            rec["Vd"].append(Vd); rec["step_time"].append(dt)
+            rec["ev_ij"].append(ev); rec["ev_ptr"].append(rec["ev_ptr"][-1] + len(ev))
+            rec["el_sha"].append(sha(s.element())); rec["q_sha"].append(sha(s.charge()))
+            count += 1
+            print(name, "step", count, "Vd", Vd, "events", len(ev), "dt", dt, flush=True)
+        if count >= nsteps:
+            break
+    rec["pb_last"], rec["pc_last"] = s.potential_boundary(), s.potential_charge()
+    rec["element_last"] = s.element().astype(np.int8)
+    rec["ev_ij"] = np.concatenate(rec["ev_ij"]).astype(np.int32) if rec["ev_ptr"][-1] else np.zeros((0, 2), np.int32)
+    np.savez_compressed(os.path.join(OUT, name), **{k: np.asarray(v) for k, v in rec.items()})
+
+
+if __name__ == "__main__":
+    import devicekmc_b200.host as H
+    p = H.KMCParameters.from_file(REF + "parameters.txt")
+    which = sys.argv[1:] or ["step0", "ramp", "6V"]
+    if "step0" in which:
+        step0()
+    if "ramp" in which:
+        trajectory("s_traj_ramp.npz", list(zip(p.V_switch, p.t_switch)), 12)
+    if "6V" in which:
+        trajectory("s_traj_6V.npz", [(6.0, 1.0)], 6)
