@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the DeviceKMC field-and-rate hot path on B200 (BASELINE.json metric:
+"KMC steps/sec at 1/2/4/8 B200 (1M sites); CG SpMV HBM GB/s vs peak").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm on the box's host cores
+
+One "step" = one pass of kmc_main.cpp:175-279 with solve_potential = perturb_structure = 1:
+updateCharge -> K assembly + CG -> pairwise Coulomb sum -> rate table -> residence-time loop.
+Prints ONE JSON line (rank 0).  The oracle (oracle/) is used only by the cpu_baseline /
+--impl reference legs, as the thing timed on the CPU — never inside the GPU path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kmc_steps_per_sec"
+UNIT = "steps/s"
+
+
+def workload(name):
+    from devicekmc_b200 import structures as S
+    from devicekmc_b200.host import KMCParameters
+    ny, nz = S.WORKLOADS[name]
+    el, x, y, z, lat, nc = S.tile_device(ny, nz)
+    p = KMCParameters(lattice=tuple(lat), num_atoms_contact=nc, num_atoms_first_layer=nc)
+    return el, x, y, z, lat, nc, p
+
+
+def substoichiometric(el, p):
+    """Device::makeSubstoichiometric (Device.cpp:202-233) on host arrays, reference random stream"""
+    from devicekmc_b200.host import RandomNumberGenerator, DEFECT, OXYGEN_DEFECT, O_EL, VACANCY
+    rng = RandomNumberGenerator(p.rnd_seed)
+    atom_ind = np.nonzero((el != DEFECT) & (el != OXYGEN_DEFECT))[0]
+    n_add = int(p.initial_vacancy_concentration * np.count_nonzero(el == O_EL))
+    el = el.copy()
+    while n_add > 0:
+        u = rng.getRandomNumbers(4096)
+        for loc in (u * len(atom_ind)).astype(np.int64):
+            if n_add > 0 and el[atom_ind[loc]] == O_EL:
+                el[atom_ind[loc]] = VACANCY
+                n_add -= 1
+    return el
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------- CPU arm
+def cpu_step_sample(name, threads=None, pair_rows=None, Vd=10.0):
+    """One KMC step of the oracle (CPU restatement of the reference's algorithm, sparse K) on
+    the same workload.  The pairwise O(N*N_charged) sum is timed on a bounded sample of target
+    rows and scaled to N.  The reference's own CPU build (oracle/_ref) cannot run this workload:
+    it allocates a dense N x N K (potential_solver.cpp:301) = 8.5 TB at 1 M sites."""
+    from oracle import oracle as O
+    threads = threads or os.cpu_count()
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    el, x, y, z, lat, nc, p = workload(name)
+    el = substoichiometric(el, p)
+    N = len(x)
+    from devicekmc_b200.host import DEFAULT_LAYERS
+    t = {}
+    t0 = time.perf_counter(); nb, nn = O.neighbor_list(x, y, z, lat, p.pbc, p.nn_dist, method=1); t["init_neighbors"] = time.perf_counter() - t0
+    layer = O.site_layers(x, [l.start_x for l in DEFAULT_LAYERS], [l.end_x for l in DEFAULT_LAYERS])
+    E = np.array([[l.E_gen_0, l.E_rec_1, l.E_diff_2, l.E_diff_3] for l in DEFAULT_LAYERS])
+    t0 = time.perf_counter(); q = O.update_charge(nb, el, p.metals, np.zeros(N, np.int32)); t["charge"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pb, info = O.background_potential(nb, nc, nc, el, q, p.metals, p.high_G, p.low_G, Vd, tol=1e-12, refine=1)
+    t["potential_boundary"] = time.perf_counter() - t0
+    ncharged = int(np.count_nonzero(q))
+    rows = pair_rows or max(1024, min(N, int(2.0e8 * threads / 8 / max(ncharged, 1))))
+    rows = min(rows, N)
+    r0 = (N - rows) // 2
+    t0 = time.perf_counter(); pc_rows = O.poisson_gridless(x, y, z, lat, p.pbc, q, p.sigma, p.k, rows=(r0, r0 + rows))
+    t_pair_sample = time.perf_counter() - t0
+    t["pairwise_sample"] = t_pair_sample
+    t["pairwise_scaled"] = t_pair_sample * N / rows
+    pc = np.zeros(N); pc[r0:r0 + rows] = pc_rows
+    t0 = time.perf_counter()
+    et, ep = O.rate_table(nb, layer, lat, p.pbc, p.background_temp, p.freq, p.sigma, p.k, x, y, z, pb, pc, el, q, E)
+    t["rate_table"] = time.perf_counter() - t0
+    rng = O.Rng(1)
+    t0 = time.perf_counter(); tt, ev, el2, q2 = O.kmc_events(nb, et, ep, el, q, p.freq, rng); t["event_loop"] = time.perf_counter() - t0
+    step_s = t["charge"] + t["potential_boundary"] + t["pairwise_scaled"] + t["rate_table"] + t["event_loop"]
+    sample = (f"oracle port, 1 step of {name} (N={N}, N_charged={ncharged}, {int(info[0])} CG its, {len(ev)} events); "
+              f"pairwise timed on {rows} of {N} target rows and scaled; all other stages in full")
+    return 1.0 / step_s, threads, sample, t
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, smp, tim = [], "", {}
+    for s in range(max(1, min(args.steps, 2))):
+        v, cores, smp, tim = cpu_step_sample(args.workload)
+        vals.append(v)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "Vd": 10.0},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": smp,
+                             "stage_seconds": {k: round(v, 4) for k, v in tim.items()},
+                             "why_port": "the reference CPU build needs a dense N x N K (8.5 TB at 1M sites)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- GPU arm
+def gpu_arm(args):
+    import torch
+    import devicekmc_b200 as D
+    from devicekmc_b200._capi import check
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from devicekmc_b200 import slab
+        return slab.bench_multi_gpu(args, METRIC, UNIT)
+    torch.cuda.set_device(local)
+    el, x, y, z, lat, nc, p = workload(args.workload)
+    el = substoichiometric(el, p)
+    t0 = time.perf_counter()
+    dev = D.Device([], p, arrays=(el, x, y, z))
+    sim = D.KMCProcess(dev, p.freq)
+    buf = D.GPUBuffers(sim.layers, sim.site_layer, sim.freq, dev, p.metals)
+    buf.sync_HostToGPU(dev)
+    sp = buf.sparsity(nc, nc)
+    torch.cuda.synchronize()
+    init_s = time.perf_counter() - t0
+    Vd = args.vd
+    stats = []
+
+    def step(e2e=False):
+        if e2e:
+            buf.sync_HostToGPU(dev)
+        dev.updateCharge(buf, p.metals)
+        o = dev.updatePotential(buf, p, Vd, n_contact=nc)
+        sim.executeKMCStep(buf, dev)
+        if e2e:
+            buf.sync_GPUToHost(dev)
+        i = sim.last_info
+        o.update(events=i.n_events, fallbacks=i.n_exact_fallbacks, rate_ms=i.rate_ms, loop_ms=i.loop_ms)
+        return o
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = dev.ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        stats.append(step())
+    e1.record(); e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = dev.ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    value = args.steps / (ms * 1e-3)
+
+    # e2e: same step through the host-facing API with HOST buffers (pinned H2D in, D2H out)
+    for _ in range(1):
+        step(e2e=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(e2e=True)
+    e1.record(); e1.synchronize()
+    e2e_value = args.steps / (e0.elapsed_time(e1) * 1e-3)
+
+    # ---- rooflines, measured live with CUDA events on the launching stream
+    lib = dev.ctx.lib
+    hbm_peak, peak_src = measured_peaks()
+    m, nnz = sp.m, sp.nnz
+    val = torch.empty(nnz, dtype=torch.float64, device="cuda"); rhs = torch.empty(m, dtype=torch.float64, device="cuda")
+    check(lib.dkmc_assemble_K(dev.ctx.h, C.byref(sp), dev.N, nc, nc, Vd, p.high_G, p.low_G, buf.site_element.data_ptr(),
+                              buf.site_charge.data_ptr(), buf.metal_types.data_ptr(), len(p.metals), val.data_ptr(), rhs.data_ptr()))
+    xv = torch.rand(m, dtype=torch.float64, device="cuda"); yv = torch.empty_like(xv)
+    reps = 50
+    for _ in range(5):
+        check(lib.dkmc_spmv(dev.ctx.h, m, nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xv.data_ptr(), yv.data_ptr()))
+    e0.record()
+    for _ in range(reps):
+        check(lib.dkmc_spmv(dev.ctx.h, m, nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xv.data_ptr(), yv.data_ptr()))
+    e1.record(); e1.synchronize()
+    spmv_ms = e0.elapsed_time(e1) / reps
+    spmv_bytes = 12.0 * nnz + 20.0 * m
+    spmv_gbs = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    fp64 = C.c_double(0)
+    check(lib.dkmc_probe_fp64_tflops(dev.ctx.h, C.byref(fp64)))
+    ncharged = int((buf.site_charge != 0).sum().item())
+    pair_ms = float(np.median([s["pairwise_ms"] for s in stats]))
+    pairs = float(dev.N) * ncharged - ncharged
+    pair_tflops = 200.0 * pairs / (pair_ms * 1e-3) / 1e12
+    # scan primitive over the N*nn rate table
+    n_tab = dev.N * buf.nn_
+    tab = torch.rand(n_tab, dtype=torch.float64, device="cuda"); cum = torch.empty_like(tab)
+    for _ in range(3):
+        check(lib.dkmc_inclusive_scan(dev.ctx.h, n_tab, tab.data_ptr(), cum.data_ptr()))
+    e0.record()
+    for _ in range(10):
+        check(lib.dkmc_inclusive_scan(dev.ctx.h, n_tab, tab.data_ptr(), cum.data_ptr()))
+    e1.record(); e1.synchronize()
+    scan_ms = e0.elapsed_time(e1) / 10
+    rate_ms = float(np.median([s["rate_ms"] for s in stats]))
+    med = lambda k: float(np.median([s[k] for s in stats]))
+    shares = {"assemble": med("assemble_ms"), "cg_solve": med("solve_ms"), "pairwise": pair_ms, "rate_table": rate_ms,
+              "event_loop": med("loop_ms")}
+    rooflines = {
+        "spmv": {"bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
+                 "traffic": None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "peak_source": peak_src},
+        "pairwise": {"bound": "fp64", "achieved": pair_tflops, "peak": fp64.value, "unit": "TFLOP/s",
+                     "frac": pair_tflops / fp64.value if fp64.value else None, "traffic": None,
+                     "flops_per_pair": 200, "pairs": pairs, "ms_per_launch": pair_ms,
+                     "peak_source": "measured here: DFMA-chain probe (dkmc_probe_fp64_tflops)"},
+        "rate_table": {"bound": "hbm", "achieved": 16.0 * n_tab / (rate_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                       "unit": "GB/s", "frac": 16.0 * n_tab / (rate_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+        "scan": {"bound": "hbm", "achieved": 16.0 * n_tab / (scan_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": 16.0 * n_tab / (scan_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+    }
+    dominant = max(shares, key=shares.get)
+    roof_key = {"pairwise": "pairwise", "cg_solve": "spmv", "assemble": "spmv", "rate_table": "rate_table",
+                "event_loop": "rate_table"}[dominant]
+    roofline = dict(rooflines[roof_key]); roofline["kernel"] = roof_key; roofline["dominant_stage"] = dominant
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cores, smp, tim = cpu_step_sample(args.workload)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": smp,
+               "stage_seconds": {k: round(t, 4) for k, t in tim.items()}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "sites": dev.N, "nn": buf.nn_, "interior_rows": m, "nnz": nnz,
+                       "n_charged": ncharged, "Vd": Vd, "l2": "inputs larger than L2 (matrix 12*nnz bytes, rate table 16*N*nn bytes)",
+                       "init_seconds": round(init_s, 3)},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": buf.h2d_bytes(), "d2h_bytes_per_step": buf.d2h_bytes()},
+            "roofline": roofline, "rooflines": rooflines, "stage_ms": shares,
+            "per_step": {"events": [s["events"] for s in stats], "exact_fallbacks": [s["fallbacks"] for s in stats],
+                         "cg_iterations": [s["cg_iterations"] for s in stats]},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tiled_1M")
+    ap.add_argument("--vd", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,12 +34,13 @@ class Sparsity(C.Structure):
 
 class SolverOpts(C.Structure):
     _fields_ = [("rel_tol", C.c_double), ("max_iter", C.c_int), ("refine_rounds", C.c_int),
-                ("check_every", C.c_int)]
+                ("check_every", C.c_int), ("cluster_precond", C.c_int), ("refine_tol", C.c_double),
+                ("est_tol", C.c_double)]
 
 
 class SolveInfo(C.Structure):
     _fields_ = [("iterations", C.c_int), ("refinements", C.c_int), ("rel_residual", C.c_double),
-                ("assemble_ms", C.c_double), ("solve_ms", C.c_double)]
+                ("assemble_ms", C.c_double), ("solve_ms", C.c_double), ("est_error", C.c_double)]
 
 
 class StepInfo(C.Structure):
@@ -56,7 +57,7 @@ EXPORTS = [
     "dkmc_background_potential_sparse", "dkmc_assemble_K", "dkmc_spmv", "dkmc_solve_cg",
     "dkmc_poisson_gridless", "dkmc_poisson_gridless_rows", "dkmc_build_event_list",
     "dkmc_inclusive_scan", "dkmc_select_event", "dkmc_execute_kmc_step", "dkmc_kmc_step_continue",
-    "dkmc_ctx_set_exact_select", "dkmc_last_event_tables",
+    "dkmc_ctx_set_exact_select", "dkmc_last_event_tables", "dkmc_probe_fp64_tflops",
 ]
 
 _lib = None
@@ -102,6 +103,7 @@ def load() -> C.CDLL:
                                                                                        C.POINTER(StepInfo)]
         lib.dkmc_kmc_step_continue.argtypes = [vp, vp, ci, vp, ci, C.POINTER(StepInfo)]
         lib.dkmc_last_event_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        lib.dkmc_probe_fp64_tflops.argtypes = [vp, C.POINTER(cd)]
         lib.dkmc_get_gpu_info.argtypes = [C.c_char_p, ci, ci]
         lib.dkmc_set_gpu.argtypes = [ci]
         lib.dkmc_device_count.argtypes = [C.POINTER(ci)]

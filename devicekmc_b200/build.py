@@ -27,6 +27,7 @@ SOURCES = {
     "solver.cu": [],
     "pairwise.cu": [],
     "events.cu": ["-fmad=false"],
+    "probes.cu": [],
 }
 
 

@@ -145,8 +145,11 @@ void dkmc_default_solver_opts(dkmc_solver_opts *o) {
     if (!o) return;
     o->rel_tol = 1e-12;
     o->max_iter = 20000;
-    o->refine_rounds = 2;
+    o->refine_rounds = 4;
     o->check_every = 32;
+    o->cluster_precond = 1;
+    o->refine_tol = 1e-6;
+    o->est_tol = 1e-14;
 }
 
 }  // extern "C"

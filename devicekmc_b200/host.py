@@ -319,10 +319,16 @@ class Device:
             _ptr(gpubuf.metal_types), gpubuf.num_metal_types_, _ptr(gpubuf.site_potential_boundary),
             C.byref(opts) if opts is not None else None, C.byref(info))
         check(st, allow=(_capi.DKMC_ERR_NOT_CONVERGED,))
+        torch = _torch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         check(lib.dkmc_poisson_gridless(self.ctx.h, self.pbc, gpubuf.N_, _ptr(gpubuf.lattice), _ptr(gpubuf.sigma),
                                         _ptr(gpubuf.k), _ptr(gpubuf.site_x), _ptr(gpubuf.site_y), _ptr(gpubuf.site_z),
                                         _ptr(gpubuf.site_charge), _ptr(gpubuf.site_potential_charge)))
-        return {"cg_iterations": info.iterations, "cg_rel_residual": info.rel_residual,
+        e1.record()
+        e1.synchronize()
+        return {"pairwise_ms": e0.elapsed_time(e1), "cg_iterations": info.iterations, "cg_rel_residual": info.rel_residual,
+                "cg_est_error": info.est_error, "cg_refinements": info.refinements,
                 "cg_converged": st == _capi.DKMC_OK, "assemble_ms": info.assemble_ms, "solve_ms": info.solve_ms}
 
 

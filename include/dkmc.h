@@ -101,14 +101,19 @@ int dkmc_update_charge(dkmc_ctx *ctx, const int *d_site_element, int *d_site_cha
 typedef struct {
     double rel_tol;      /* CG stop: ||r||_D^-1 <= rel_tol * ||b||_D^-1   (default 1e-12) */
     int max_iter;        /* per CG run (default 20000) */
-    int refine_rounds;   /* double-double residual refinements (default 2) */
+    int refine_rounds;   /* max restarts on the double-double residual (default 4) */
     int check_every;     /* iterations between host convergence polls (default 32) */
+    int cluster_precond; /* 1 (default): add one coarse unknown per uncharged-vacancy cluster to the
+                            Jacobi preconditioner; 0: plain Jacobi as the reference */
+    double refine_tol;   /* relative tolerance of each restart's correction solve (default 1e-6) */
+    double est_tol;      /* restart while max|M^-1 r_true| / max|x| exceeds this (default 1e-14) */
 } dkmc_solver_opts;
 typedef struct {
     int iterations;        /* total CG iterations incl. refinement runs */
     int refinements;       /* refinement rounds executed */
     double rel_residual;   /* final double-double ||b - A x||_2 / ||b||_2 */
     double assemble_ms, solve_ms; /* device time of the two phases */
+    double est_error;      /* max|M^-1 (b - A x)| / max|x| of the returned solution */
 } dkmc_solve_info;
 void dkmc_default_solver_opts(dkmc_solver_opts *o);
 int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int nn,
@@ -188,6 +193,11 @@ int dkmc_kmc_step_continue(dkmc_ctx *ctx, const double *uniforms, int n_uniforms
 int dkmc_ctx_set_exact_select(dkmc_ctx *ctx, int mode);
 /* device pointers of the last step's event tables (valid until the next step) */
 int dkmc_last_event_tables(dkmc_ctx *ctx, const int **d_event_type, const double **d_event_prob);
+
+/* Measurement aid (no reference counterpart): achievable FP64 FMA throughput of this GPU in
+ * TFLOP/s (8 independent DFMA chains per thread on every SM) — the roofline denominator of the
+ * pairwise sum, which MEASURED_PEAKS.json does not carry. */
+int dkmc_probe_fp64_tflops(dkmc_ctx *ctx, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -194,6 +194,46 @@ def test_background_potential(sim0, O, golden_step0, torch, Vd):
     assert rel_inf(buf.site_potential_boundary.cpu().numpy(), ref) <= TOL
 
 
+def test_background_potential_cluster_preconditioner(sim0, O, torch):
+    """plain Jacobi (the reference's preconditioner) and Jacobi + cluster coarse space reach the
+    same solution; the coarse space needs far fewer iterations"""
+    import devicekmc_b200 as D
+    p, dev, sim, buf = sim0
+    nc = p.num_atoms_contact
+    # plant uncharged-vacancy clusters: turn a few oxygen neighbours of vacancies into vacancies
+    el = dev.site_element.copy()
+    nb = dev.neigh_idx.reshape(dev.N, -1)
+    vac = np.nonzero(el == D.host.VACANCY)[0][:40]
+    for v in vac:
+        for j in nb[v]:
+            if j >= 0 and el[j] == D.host.O_EL:
+                el[j] = D.host.VACANCY
+                break
+    saved = dev.site_element.copy()
+    dev.site_element[...] = el
+    try:
+        buf.sync_HostToGPU(dev)
+        dev.updateCharge(buf, p.metals)
+        q = buf.site_charge.cpu().numpy()
+        assert np.count_nonzero((el == D.host.VACANCY) & (q == 0)) >= 20
+        ref, _ = O.background_potential(nb, nc, nc, el, q, p.metals, p.high_G, p.low_G, 8.0, refine=3)
+        its = {}
+        for flag in (1, 0):
+            o = D.SolverOpts()
+            dev.ctx.lib.dkmc_default_solver_opts(C.byref(o))
+            o.cluster_precond = flag
+            o.refine_rounds = 4
+            buf.site_potential_boundary.zero_()
+            out = dev.updatePotential(buf, p, 8.0, n_contact=nc, opts=o)
+            assert out["cg_converged"]
+            assert rel_inf(buf.site_potential_boundary.cpu().numpy(), ref) <= TOL, flag
+            its[flag] = out["cg_iterations"]
+        assert its[1] < its[0]
+    finally:
+        dev.site_element[...] = saved
+        buf.sync_HostToGPU(dev)
+
+
 # ------------------------------------------------------------------ a6 pairwise
 @pytest.mark.parametrize("pbc", [0, 1])
 def test_poisson_gridless(base_case, O, golden_step0, torch, pbc):
