@@ -9,6 +9,7 @@
 // bound, O(N * N_charged).
 #include "common.cuh"
 #include "scan.cuh"
+#include "erfc_coeffs.cuh"
 
 namespace dkmc {
 
@@ -65,11 +66,54 @@ __global__ void __launch_bounds__(kCompactBlock) charged_scatter_kernel(
     if (blockIdx.x == 0 && threadIdx.x == 0) *total = block_incl[nblocks - 1];
 }
 
+// ---- branch-free FP64 building blocks (MUFU seed + one third-order Newton step)
+__device__ __forceinline__ double rsqrt_fast(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a * y, y, 1.0);                 // 1 - a y^2
+    double c = fma(0.375, e, 0.5) * e;              // e/2 + 3 e^2/8
+    return fma(y, c, y);
+}
+__device__ __forceinline__ double rcp_fast(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    double c = fma(e, e, e);
+    return fma(y, c, y);
+}
+// exp(-s) for 0 <= s <= 700 (no denormal results in that range)
+__device__ __forceinline__ double exp_neg_fast(double s) {
+    const double kMagic = 6755399441055744.0;      // 1.5 * 2^52: rounds to nearest integer
+    double tmp = fma(-s, 1.4426950408889634, kMagic);
+    int n = __double2loint(tmp);
+    double nd = tmp - kMagic;
+    double r = fma(nd, -6.93147180369123816490e-01, -s);
+    r = fma(nd, -1.90821492927058770002e-10, r);
+    double p = kExpC[kExpDeg];
+#pragma unroll
+    for (int i = kExpDeg - 1; i >= 0; --i) p = fma(p, r, kExpC[i]);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+// erfc(t) / 1  for t >= 0, relative error ~3e-15 (tools/fit_erfcx.py): exp(-t^2) * erfcx(t)
+__device__ __forceinline__ double erfc_fast(double t) {
+    double w = rcp_fast(t + kErfcxK);
+    double v = fma(kErfcxB, w, kErfcxA);
+    double g = kErfcxC[kErfcxDeg];
+#pragma unroll
+    for (int i = kErfcxDeg - 1; i >= 0; --i) g = fma(g, v, kErfcxC[i]);
+    double s = fmin(t * t, 700.0);
+    double e = exp_neg_fast(s);
+    return t < 26.45 ? g * e : 0.0;  // erfc < 1e-305 beyond: contributes nothing at 1e-10
+}
+
+// phi_c[i] = k q_e sum_j q_j erfc(r_ij / (sigma sqrt 2)) / r_ij.  One target per thread, sources
+// staged in shared memory, two independent sources per iteration for ILP, no atomics.
+template <bool PBC>
 __global__ void __launch_bounds__(kPwThreads) pairwise_kernel(
     int row_begin, int row_end, const double *__restrict__ x, const double *__restrict__ y,
     const double *__restrict__ z, const int *__restrict__ n_src_ptr, const ChargedSite *__restrict__ src,
-    const int *__restrict__ src_idx, const double *__restrict__ lattice, int pbc,
-    const double *__restrict__ sigma_ptr, const double *__restrict__ k_ptr, double *__restrict__ out) {
+    const int *__restrict__ src_idx, const double *__restrict__ lattice, const double *__restrict__ sigma_ptr,
+    const double *__restrict__ k_ptr, double *__restrict__ out) {
     __shared__ ChargedSite tile[kPwTile];
     __shared__ int tile_idx[kPwTile];
     const int i = row_begin + blockIdx.x * kPwThreads + threadIdx.x;
@@ -78,8 +122,25 @@ __global__ void __launch_bounds__(kPwThreads) pairwise_kernel(
     const int nsrc = *n_src_ptr;
     const double sigma = *sigma_ptr, kc = *k_ptr;
     const double ly = lattice[1], lz = lattice[2];
-    const double denom = sigma * sqrt(2.0);
-    double acc = 0.0;
+    const double inv_ly = 1.0 / ly, inv_lz = 1.0 / lz;
+    const double cscale = 1e-10 / (sigma * sqrt(2.0));  // t = r[Angstrom] * cscale
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double acc0 = 0.0, acc1 = 0.0;
+
+    auto pair_term = [&](const ChargedSite &s, int sidx) -> double {
+        double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
+        if (PBC) {
+            dy = fma(-rint(dy * inv_ly), ly, dy);
+            dz = fma(-rint(dz * inv_lz), lz, dz);
+        }
+        double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        double rinv = rsqrt_fast(r2);
+        double r = r2 * rinv;
+        double term = s.q * erfc_fast(r * cscale) * rinv;
+        term = (r2 == 0.0) ? s.q * inf : term;   // coincident sites: the reference divides by zero
+        return (sidx == i) ? 0.0 : term;         // i != j (potential_solver.cpp:422)
+    };
+
     for (int t0 = 0; t0 < nsrc; t0 += kPwTile) {
         const int nt = min(kPwTile, nsrc - t0);
         __syncthreads();
@@ -88,21 +149,15 @@ __global__ void __launch_bounds__(kPwThreads) pairwise_kernel(
             tile_idx[t] = src_idx[t0 + t];
         }
         __syncthreads();
-        if (valid) {
-            for (int t = 0; t < nt; ++t) {
-                if (tile_idx[t] == i) continue;  // i != j (potential_solver.cpp:422)
-                const ChargedSite s = tile[t];
-                double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
-                if (pbc) {
-                    double fy = dy / ly; fy -= round(fy); dy = fy * ly;
-                    double fz = dz / lz; fz -= round(fz); dz = fz * lz;
-                }
-                double r = 1e-10 * sqrt(dx * dx + dy * dy + dz * dz);
-                acc += s.q * erfc(r / denom) * kc * kElementaryCharge / r;
-            }
+        int t = 0;
+        for (; t + 1 < nt; t += 2) {
+            acc0 += pair_term(tile[t], tile_idx[t]);
+            acc1 += pair_term(tile[t + 1], tile_idx[t + 1]);
         }
+        if (t < nt) acc0 += pair_term(tile[t], tile_idx[t]);
     }
-    if (valid) out[i] = acc;
+    // rinv is in 1/Angstrom: 1e10 converts to 1/m
+    if (valid) out[i] = (acc0 + acc1) * (kc * kElementaryCharge * 1e10);
 }
 
 }  // namespace dkmc
@@ -134,8 +189,13 @@ int dkmc_poisson_gridless_rows(dkmc_ctx *ctx, int pbc, int N, const double *d_la
     DKMC_LAUNCH(ctx, charged_scatter_kernel, nb, kCompactBlock, 0, N, nb, d_site_charge, d_x, d_y, d_z, counts, incl,
                 src, src_idx, total);
     const int rows = row_end - row_begin;
-    DKMC_LAUNCH(ctx, pairwise_kernel, ceil_div(rows, kPwThreads), kPwThreads, 0, row_begin, row_end, d_x, d_y, d_z,
-                total, src, src_idx, d_lattice, pbc, d_sigma, d_k, d_site_potential_charge);
+    if (pbc) {
+        DKMC_LAUNCH(ctx, pairwise_kernel<true>, ceil_div(rows, kPwThreads), kPwThreads, 0, row_begin, row_end, d_x, d_y,
+                    d_z, total, src, src_idx, d_lattice, d_sigma, d_k, d_site_potential_charge);
+    } else {
+        DKMC_LAUNCH(ctx, pairwise_kernel<false>, ceil_div(rows, kPwThreads), kPwThreads, 0, row_begin, row_end, d_x, d_y,
+                    d_z, total, src, src_idx, d_lattice, d_sigma, d_k, d_site_potential_charge);
+    }
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
     return DKMC_OK;
 }

@@ -18,8 +18,9 @@
 namespace dkmc {
 
 constexpr int kSpmvThreads = 256;
-constexpr int kSpmvTile = 2048;             // nnz per tile (by row start)
-constexpr int kSpmvCap = kSpmvTile + 256;   // shared products per block
+constexpr int kSpmvCap = 2048;              // shared products per block = 256 threads x 8
+constexpr int kSpmvTile = kSpmvCap - 64;    // nnz per tile by row start: with rows <= 63 long a
+                                            // tile (+1 alignment slot) always fits one pass
 constexpr int kVecThreads = 256;
 constexpr int kMaxPartials = 1 << 16;
 
@@ -97,50 +98,58 @@ __global__ void tile_rows_kernel(int m, int num_tiles, const int *__restrict__ r
 
 // y = A x over one nnz tile per block.  MODE 0: y only.  MODE 1: also dot(w, y) -> *dot_out.
 // MODE 2: y = b - A x (residual) and rr = sum (y^2 * dinv) -> *dot_out.
+// Phase 1 streams the tile's val/col with 16-byte loads, all 8 elements of a thread in flight at
+// once (one DRAM round trip per tile), gathers x through the read-only path and parks the
+// products in shared memory; phase 2 adds each row's products in CSR order.
 template <int MODE>
 __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(
-    int m, const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
+    int m, int nnz, const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
     const double *__restrict__ x, double *__restrict__ y, const int *__restrict__ tile_row,
     const double *__restrict__ w, const double *__restrict__ dinv, double *partials, unsigned int *counter,
     double *dot_out, const int *done_flag) {
-    __shared__ double prod[kSpmvCap];
+    __shared__ __align__(16) double prod[kSpmvCap];
     __shared__ double red[32];
     if (done_flag && *done_flag) return;
     const int r0 = tile_row[blockIdx.x], r1 = tile_row[blockIdx.x + 1];
     double local = 0.0;
     if (r0 < r1) {
         const int k0 = row_ptr[r0], k1 = row_ptr[r1];
-        const int cnt = k1 - k0;
-        if (cnt <= kSpmvCap) {
-            // phase 1: coalesced stream of val/col, gather x through the read-only path
-            for (int base = 0; base < cnt; base += kSpmvThreads * 4) {
+        const int ka = k0 & ~1;  // even start: 16-byte aligned double2 / 8-byte aligned int2
+        // row bounds of this thread's first row, requested before the big loads
+        int my_r = r0 + threadIdx.x, ra = 0, rb = 0;
+        if (my_r < r1) { ra = row_ptr[my_r]; rb = row_ptr[my_r + 1]; }
+        if (k1 - ka <= kSpmvCap) {
+            // two batches of four 8-byte/4-byte loads per thread (32 registers -> 8 blocks per SM)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
                 double v[4];
                 int c[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    int k = base + u * kSpmvThreads + threadIdx.x;
-                    bool ok = k < cnt;
-                    v[u] = ok ? __ldcs(val + k0 + k) : 0.0;
-                    c[u] = ok ? __ldcs(col + k0 + k) : 0;
+                    int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
+                    bool ok = k < k1;
+                    v[u] = ok ? __ldcs(val + k) : 0.0;
+                    c[u] = ok ? __ldcs(col + k) : 0;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    int k = base + u * kSpmvThreads + threadIdx.x;
-                    if (k < cnt) prod[k] = v[u] * __ldg(x + c[u]);
+                    int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
+                    if (k < k1) prod[k - ka] = v[u] * __ldg(x + c[u]);
                 }
             }
             __syncthreads();
             // phase 2: each row adds its products in CSR order
-            for (int r = r0 + threadIdx.x; r < r1; r += kSpmvThreads) {
-                int a = row_ptr[r] - k0, b = row_ptr[r + 1] - k0;
+            for (int r = my_r; r < r1; r += kSpmvThreads) {
+                if (r != my_r) { ra = row_ptr[r]; rb = row_ptr[r + 1]; }
                 double s = 0.0;
-                for (int k = a; k < b; ++k) s += prod[k];
+#pragma unroll 4
+                for (int k = ra - ka; k < rb - ka; ++k) s += prod[k];
                 if (MODE == 2) { s = w[r] - s; local += s * s * dinv[r]; }
                 y[r] = s;
                 if (MODE == 1) local += w[r] * s;
             }
-        } else {  // rows longer than the staging buffer: direct path
-            for (int r = r0 + threadIdx.x; r < r1; r += kSpmvThreads) {
+        } else {  // rows too long for the staging buffer: direct path
+            for (int r = my_r; r < r1; r += kSpmvThreads) {
                 double s = 0.0;
                 for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) s += val[k] * __ldg(x + col[k]);
                 if (MODE == 2) { s = w[r] - s; local += s * s * dinv[r]; }
@@ -448,21 +457,45 @@ __global__ void __launch_bounds__(kVecThreads) cg_init_kernel(int m, const doubl
     }
 }
 
+__device__ __forceinline__ double2 ld2(const double *p, bool vec) {
+    if (vec) return *reinterpret_cast<const double2 *>(p);
+    return make_double2(p[0], p[1]);
+}
+__device__ __forceinline__ void st2(double *p, double2 v, bool vec) {
+    if (vec) *reinterpret_cast<double2 *>(p) = v;
+    else { p[0] = v.x; p[1] = v.y; }
+}
+__device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // alpha = rz/pAp; x += alpha p; r_new = r_old - alpha Ap; rz_new = r_new . M^-1 r_new;
 // last block: beta, convergence.  r is ping-ponged so that cluster members can be re-formed.
-__global__ void __launch_bounds__(kVecThreads) cg_update_kernel(int m, double *__restrict__ x, const double *r_old,
-                                                               double *r_new, const double *__restrict__ p,
+// Two elements per thread per pass, 16-byte loads.
+__global__ void __launch_bounds__(kVecThreads) cg_update_kernel(int m, double *x, const double *r_old,
+                                                               double *r_new, const double *p,
                                                                const double *Ap, Precond P, double *partials,
                                                                CgScalars *sc) {
     __shared__ double red[32];
     if (sc->done) return;
     const double alpha = sc->rz / sc->pAp;
+    const bool vx = aligned16(x);
     double local = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        x[i] += alpha * p[i];
-        double ri = r_old[i] - alpha * Ap[i];
-        r_new[i] = ri;
-        local += ri * precond_apply_updated(P, i, ri, r_old, Ap, alpha);
+    const int n2 = (m + 1) >> 1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += gridDim.x * blockDim.x) {
+        const int i = 2 * j;
+        if (i + 1 < m) {
+            double2 p2 = ld2(p + i, true), r2 = ld2(r_old + i, true), a2 = ld2(Ap + i, true), x2 = ld2(x + i, vx);
+            x2.x += alpha * p2.x; x2.y += alpha * p2.y;
+            r2.x -= alpha * a2.x; r2.y -= alpha * a2.y;
+            st2(x + i, x2, vx);
+            st2(r_new + i, r2, true);
+            local += r2.x * precond_apply_updated(P, i, r2.x, r_old, Ap, alpha);
+            local += r2.y * precond_apply_updated(P, i + 1, r2.y, r_old, Ap, alpha);
+        } else {
+            x[i] += alpha * p[i];
+            double ri = r_old[i] - alpha * Ap[i];
+            r_new[i] = ri;
+            local += ri * precond_apply_updated(P, i, ri, r_old, Ap, alpha);
+        }
     }
     double tot = block_sum(local, red);
     if (grid_sum_finish(tot, partials, &sc->cnt_b, &sc->rz_new, red)) {
@@ -476,12 +509,22 @@ __global__ void __launch_bounds__(kVecThreads) cg_update_kernel(int m, double *_
 }
 
 // p = M^-1 r + beta p   (skipped once converged)
-__global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(int m, const double *r, Precond P,
-                                                                  double *__restrict__ p, const CgScalars *sc) {
+__global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(int m, const double *r, Precond P, double *p,
+                                                                  const CgScalars *sc) {
     if (sc->done) return;
     const double beta = sc->beta;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
-        p[i] = precond_apply(P, i, r[i], r) + beta * p[i];
+    const int n2 = (m + 1) >> 1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += gridDim.x * blockDim.x) {
+        const int i = 2 * j;
+        if (i + 1 < m) {
+            double2 r2 = ld2(r + i, true), p2 = ld2(p + i, true);
+            p2.x = precond_apply(P, i, r2.x, r) + beta * p2.x;
+            p2.y = precond_apply(P, i + 1, r2.y, r) + beta * p2.y;
+            st2(p + i, p2, true);
+        } else {
+            p[i] = precond_apply(P, i, r[i], r) + beta * p[i];
+        }
+    }
 }
 
 // out = v . M^-1 v   (true-residual norm in the preconditioner's metric)
@@ -533,8 +576,8 @@ static int get_tiling(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const
 }
 
 static int vec_grid(const dkmc_ctx *ctx, int m) {
-    int g = ceil_div(m, kVecThreads);
-    int cap = ctx->num_sms * 8;
+    int g = ceil_div((m + 1) / 2, kVecThreads);
+    int cap = ctx->num_sms * 16;
     return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
@@ -596,12 +639,12 @@ static int build_clusters(dkmc_ctx *ctx, int m, int NL, const unsigned char *cls
 }
 
 // Preconditioned CG on A x = b starting from x (in/out).  w.P must be set.
-static int run_pcg(dkmc_ctx *ctx, int m, const int *d_row_ptr, const int *d_col, const double *d_val,
+static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                    const double *d_b, double *d_x, const CgWork &w, double tol, int max_iter, int check_every,
                    int *iters_out, int *converged, double *bb_out) {
     const int vg = vec_grid(ctx, m);
     // r = b - A x, then z/p/rz/bb
-    DKMC_LAUNCH(ctx, spmv_tile_kernel<2>, w.num_tiles, kSpmvThreads, 0, m, d_row_ptr, d_col, d_val, d_x, w.r[0],
+    DKMC_LAUNCH(ctx, spmv_tile_kernel<2>, w.num_tiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, w.r[0],
                 w.tile_row, d_b, w.dinv, w.partials, &w.sc->cnt_c, &w.sc->resnorm2, (const int *)nullptr);
     DKMC_LAUNCH(ctx, cg_init_kernel, vg, kVecThreads, 0, m, w.r[0], d_b, w.P, w.p, tol, max_iter, w.partials, w.sc);
     CgScalars h;
@@ -610,7 +653,7 @@ static int run_pcg(dkmc_ctx *ctx, int m, const int *d_row_ptr, const int *d_col,
     if (check_every < 1) check_every = 1;
     while (true) {
         for (int k = 0; k < check_every; ++k) {
-            DKMC_LAUNCH(ctx, spmv_tile_kernel<1>, w.num_tiles, kSpmvThreads, 0, m, d_row_ptr, d_col, d_val, w.p,
+            DKMC_LAUNCH(ctx, spmv_tile_kernel<1>, w.num_tiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, w.p,
                         w.Ap, w.tile_row, w.p, (const double *)nullptr, w.partials, &w.sc->cnt_c, &w.sc->pAp,
                         &w.sc->done);
             DKMC_LAUNCH(ctx, cg_update_kernel, vg, kVecThreads, 0, m, d_x, w.r[cur], w.r[cur ^ 1], w.p, w.Ap, w.P,
@@ -675,10 +718,9 @@ static int true_residual(dkmc_ctx *ctx, int m, const int *d_row_ptr, const int *
 static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
                          const double *d_val, const double *d_rhs, double *d_x, CgWork &w,
                          const dkmc_solver_opts &o, dkmc_solve_info *info) {
-    (void)nnz;
     int iters = 0, conv = 0, total = 0, rc;
     double bb0 = 0.0, rel = 0.0, est = 0.0;
-    if ((rc = run_pcg(ctx, m, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o.rel_tol, o.max_iter, o.check_every, &iters, &conv, &bb0))) return rc;
+    if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o.rel_tol, o.max_iter, o.check_every, &iters, &conv, &bb0))) return rc;
     total += iters;
     bool all_conv = conv != 0;
     const int vg = vec_grid(ctx, m);
@@ -690,7 +732,7 @@ static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, co
     if ((rc = true_residual(ctx, m, d_row_ptr, d_col, d_val, d_rhs, d_x, w, bb0, &rel, &est))) return rc;
     while (rounds < o.refine_rounds && est > o.est_tol) {
         DKMC_LAUNCH(ctx, fill_kernel, vg, kVecThreads, 0, m, 0.0, w.e);
-        if ((rc = run_pcg(ctx, m, d_row_ptr, d_col, d_val, w.res, w.e, w, o.refine_tol, o.max_iter, o.check_every, &iters, &conv, nullptr))) return rc;
+        if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, w.res, w.e, w, o.refine_tol, o.max_iter, o.check_every, &iters, &conv, nullptr))) return rc;
         total += iters;
         DKMC_LAUNCH(ctx, axpy_kernel, vg, kVecThreads, 0, m, 1.0, w.e, d_x);
         ++rounds;
@@ -718,7 +760,7 @@ int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_
     const int *tile_row;
     int num_tiles, rc;
     if ((rc = get_tiling(ctx, m, nnz, d_row_ptr, &tile_row, &num_tiles))) return rc;
-    DKMC_LAUNCH(ctx, spmv_tile_kernel<0>, num_tiles, kSpmvThreads, 0, m, d_row_ptr, d_col, d_val, d_x, d_y, tile_row,
+    DKMC_LAUNCH(ctx, spmv_tile_kernel<0>, num_tiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, d_y, tile_row,
                 (const double *)nullptr, (const double *)nullptr, (double *)nullptr, (unsigned int *)nullptr,
                 (double *)nullptr, (const int *)nullptr);
     return DKMC_OK;
