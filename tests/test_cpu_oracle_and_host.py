@@ -194,7 +194,7 @@ def test_tiled_device_structure(O):
 def test_capi_library_exports_every_declared_symbol():
     from devicekmc_b200 import _capi
     hdr = open(os.path.join(ROOT, "include", "dkmc.h")).read()
-    declared = set(re.findall(r"\b(dkmc_[A-Za-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"^(?:int|void|const char \*)\s*(dkmc_[A-Za-z0-9_]+)\s*\(", hdr, flags=re.M))
     assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
     lib = C.CDLL(_capi.LIB_PATH)          # loads without a GPU; no compute call is made
     for name in declared:
