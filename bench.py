@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--workload", default="tiled_1M")
     ap.add_argument("--vd", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicated-cg", action="store_true", help="N>1: keep the CG on every rank (only the pairwise sum is sharded)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -43,6 +43,16 @@ class SolveInfo(C.Structure):
                 ("assemble_ms", C.c_double), ("solve_ms", C.c_double), ("est_error", C.c_double)]
 
 
+MAX_RANKS, MAX_HALO = 64, 64
+
+
+class DistPlan(C.Structure):
+    _fields_ = [("world", C.c_int), ("row_begin", C.c_int * MAX_RANKS), ("row_end", C.c_int * MAX_RANKS),
+                ("n_send", C.c_int), ("n_recv", C.c_int),
+                ("send_peer", C.c_int * MAX_HALO), ("send_begin", C.c_int * MAX_HALO), ("send_end", C.c_int * MAX_HALO),
+                ("recv_peer", C.c_int * MAX_HALO), ("recv_begin", C.c_int * MAX_HALO), ("recv_end", C.c_int * MAX_HALO)]
+
+
 class StepInfo(C.Structure):
     _fields_ = [("n_events", C.c_int), ("n_used", C.c_int), ("n_exact_fallbacks", C.c_int),
                 ("event_time", C.c_double), ("rate_ms", C.c_double), ("loop_ms", C.c_double)]
@@ -57,7 +67,8 @@ EXPORTS = [
     "dkmc_background_potential_sparse", "dkmc_assemble_K", "dkmc_spmv", "dkmc_solve_cg",
     "dkmc_poisson_gridless", "dkmc_poisson_gridless_rows", "dkmc_build_event_list",
     "dkmc_inclusive_scan", "dkmc_select_event", "dkmc_execute_kmc_step", "dkmc_kmc_step_continue",
-    "dkmc_ctx_set_exact_select", "dkmc_last_event_tables", "dkmc_probe_fp64_tflops",
+    "dkmc_ctx_set_exact_select", "dkmc_last_event_tables", "dkmc_probe_fp64_tflops", "dkmc_spmv_tile_nnz", "dkmc_dist_unique_id", "dkmc_dist_init",
+    "dkmc_dist_finalize", "dkmc_dist_background_potential",
 ]
 
 _lib = None
@@ -103,6 +114,11 @@ def load() -> C.CDLL:
                                                                                        C.POINTER(StepInfo)]
         lib.dkmc_kmc_step_continue.argtypes = [vp, vp, ci, vp, ci, C.POINTER(StepInfo)]
         lib.dkmc_last_event_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        lib.dkmc_dist_unique_id.argtypes = [C.c_char_p]
+        lib.dkmc_dist_init.argtypes = [vp, ci, ci, C.c_char_p]
+        lib.dkmc_dist_finalize.argtypes = [vp]
+        lib.dkmc_dist_background_potential.argtypes = [vp, C.POINTER(Sparsity), ci, ci, ci, cd, cd, cd, vp, vp, vp, ci, vp,
+                                                       C.POINTER(DistPlan), C.POINTER(SolverOpts), C.POINTER(SolveInfo)]
         lib.dkmc_probe_fp64_tflops.argtypes = [vp, C.POINTER(cd)]
         lib.dkmc_get_gpu_info.argtypes = [C.c_char_p, ci, ci]
         lib.dkmc_set_gpu.argtypes = [ci]

@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.check_call(cmd)
             relink = True
     if relink:
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs]
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lnccl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

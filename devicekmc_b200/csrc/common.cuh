@@ -50,7 +50,7 @@ enum Slot : int {
     S_SP_CNT, S_SCAN_BLOCK,
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
-    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W,
+    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED,
     S_LAST
 };
 static_assert(S_LAST <= kNumSlots, "increase kNumSlots");
@@ -94,6 +94,7 @@ struct dkmc_ctx {
         bool active = false;
     } ev;
     int exact_select = 0;
+    void *dist = nullptr;  // DistState (NCCL communicator) when running slab-partitioned
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
 };
 

@@ -1,0 +1,230 @@
+"""Slab-partitioned multi-GPU execution of the hot path: one process per GPU (torchrun),
+torch.distributed/NCCL for the plumbing.
+
+Sites are ordered x-major (structures.tile_device), so a contiguous index range is a spatial slab.
+
+  stage                     partition                          exchange (NCCL over NVLink)
+  ------------------------  ---------------------------------  --------------------------------------
+  charge state machine      replicated (integer, 30 us)        none
+  K assembly + PCG          interior rows split by nnz tiles   halo of p (contiguous index ranges to the
+                                                               two x-neighbours), 2 small all-reduces
+                                                               per iteration, all-gather of phi_b
+  pairwise Coulomb sum      target rows [i0, i1) per rank,     all-gather of phi_c (8 B per site)
+                            ALL charged sources (replicated)
+  rate table + event loop   replicated: every rank runs the    none — events are serial by construction;
+                            identical loop on the same         a per-event all-gather of rate sums costs
+                            mt19937 uniforms                   more than the whole per-event work
+
+The host-side planning (row/tile ranges, halo widths, owner of a global rate target) lives here
+and is covered by world_size-2 gloo tests on the CPU (tests/test_slab_gloo.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from typing import List, Tuple
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------- planning (pure host logic)
+def split_even(n: int, world: int) -> List[Tuple[int, int]]:
+    """contiguous [begin, end) ranges of n items over `world` ranks, sizes differing by <= 1"""
+    base, rem = divmod(n, world)
+    out, b = [], 0
+    for r in range(world):
+        e = b + base + (1 if r < rem else 0)
+        out.append((b, e))
+        b = e
+    return out
+
+
+def chunk_padded(n: int, world: int) -> int:
+    """equal chunk length c with world * c >= n (for all_gather_into_tensor)"""
+    return (n + world - 1) // world
+
+
+def split_rows_by_nnz(row_ptr: np.ndarray, world: int, tile: int) -> List[Tuple[int, int]]:
+    """interior rows split so that every rank gets the same number of `tile`-nnz SpMV tiles
+    (tiles are defined by row START, exactly as the CUDA kernel's tiling does)"""
+    m = len(row_ptr) - 1
+    nnz = int(row_ptr[m])
+    ntiles = max(1, (nnz + tile - 1) // tile)
+    tile_row = np.searchsorted(row_ptr[:m], np.arange(ntiles) * tile, side="left")
+    tile_row = np.append(tile_row, m)
+    out = []
+    for t0, t1 in split_even(ntiles, world):
+        out.append((int(tile_row[t0]), int(tile_row[t1])))
+    return out
+
+
+def halo_ranges(row_ptr: np.ndarray, col: np.ndarray, rows: List[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """per rank: [lo, hi) = the smallest contiguous column range its rows touch"""
+    out = []
+    for ra, rb in rows:
+        if rb <= ra:
+            out.append((ra, ra))
+            continue
+        c = col[row_ptr[ra]:row_ptr[rb]]
+        out.append((int(min(c.min(), ra)), int(max(c.max() + 1, rb))))
+    return out
+
+
+def halo_plan(rows: List[Tuple[int, int]], halos: List[Tuple[int, int]]):
+    """For every rank the list of (peer, begin, end) segments to RECEIVE (columns it needs that
+    another rank owns).  With x-major ordering these are one segment from each x-neighbour; for an
+    arbitrary ordering the plan degenerates to (almost) an all-gather."""
+    world = len(rows)
+    recv = [[] for _ in range(world)]
+    for r in range(world):
+        lo, hi = halos[r]
+        for q in range(world):
+            if q == r:
+                continue
+            b, e = max(lo, rows[q][0]), min(hi, rows[q][1])
+            if b < e:
+                recv[r].append((q, b, e))
+    send = [[] for _ in range(world)]
+    for r in range(world):
+        for q, b, e in recv[r]:
+            send[q].append((r, b, e))
+    return recv, send
+
+
+def owner_of_target(rank_sums: np.ndarray, u: float):
+    """the global rate-sum scan that picks the owning rank: exclusive offsets of the per-rank rate
+    sums, first rank whose inclusive sum exceeds u * total.  Returns (rank, local target, total)."""
+    incl = np.cumsum(rank_sums)
+    total = float(incl[-1])
+    number = u * total
+    r = int(np.searchsorted(incl, number, side="right"))
+    if r >= len(rank_sums):
+        return -1, 0.0, total
+    return r, number - (float(incl[r - 1]) if r > 0 else 0.0), total
+
+
+# ---------------------------------------------------------------------------- GPU execution
+class SlabSim:
+    """One rank's view of the slab-partitioned simulation."""
+
+    def __init__(self, arrays, p, rank: int, world: int, distributed_cg: bool = True):
+        import torch
+        import torch.distributed as dist
+        import devicekmc_b200 as D
+        self.torch, self.dist, self.rank, self.world, self.p = torch, dist, rank, world, p
+        el, x, y, z = arrays
+        self.dev = D.Device([], p, arrays=(el, x, y, z))
+        self.sim = D.KMCProcess(self.dev, p.freq)
+        self.buf = D.GPUBuffers(self.sim.layers, self.sim.site_layer, self.sim.freq, self.dev, p.metals)
+        N = self.dev.N
+        self.nc = p.num_atoms_contact
+        # phi_c lives in a padded buffer so that the all-gather has equal chunks
+        self.chunk = chunk_padded(N, world)
+        self._pc_full = torch.zeros(self.chunk * world, dtype=torch.float64, device="cuda")
+        self.buf.site_potential_charge = self._pc_full[:N]
+        self.i0 = min(N, rank * self.chunk)
+        self.i1 = min(N, (rank + 1) * self.chunk)
+        self.buf.sync_HostToGPU(self.dev)
+        self.sp = self.buf.sparsity(self.nc, self.nc)
+        self.dcg = None
+        if distributed_cg and world > 1:
+            from . import _dist
+            self.dcg = _dist.DistributedSolver(self)
+
+    def step(self, Vd: float):
+        import devicekmc_b200 as D
+        from ._capi import SolveInfo, check
+        dev, buf, p, lib = self.dev, self.buf, self.p, self.dev.ctx.lib
+        dev.updateCharge(buf, p.metals)
+        info = SolveInfo()
+        t0 = time.perf_counter()
+        if self.dcg is not None:
+            self.dcg.solve(Vd, info)
+        else:
+            st = lib.dkmc_background_potential_sparse(
+                dev.ctx.h, C.byref(self.sp), dev.N, buf.nn_, buf.neigh_idx.data_ptr(), self.nc, self.nc, float(Vd),
+                float(p.high_G), float(p.low_G), buf.site_element.data_ptr(), buf.site_charge.data_ptr(),
+                buf.metal_types.data_ptr(), buf.num_metal_types_, buf.site_potential_boundary.data_ptr(), None,
+                C.byref(info))
+            check(st, allow=(3,))
+        # pairwise: my target rows against all charged sources, then all-gather
+        if self.i1 > self.i0:
+            check(lib.dkmc_poisson_gridless_rows(dev.ctx.h, dev.pbc, dev.N, buf.lattice.data_ptr(), buf.sigma.data_ptr(),
+                                                 buf.k.data_ptr(), buf.site_x.data_ptr(), buf.site_y.data_ptr(),
+                                                 buf.site_z.data_ptr(), buf.site_charge.data_ptr(), self.i0, self.i1,
+                                                 self._pc_full.data_ptr()))
+        if self.world > 1:
+            mine = self._pc_full[self.rank * self.chunk:(self.rank + 1) * self.chunk].clone()
+            self.dist.all_gather_into_tensor(self._pc_full, mine)
+        t = self.sim.executeKMCStep(buf, dev)
+        return {"cg_iterations": info.iterations, "solve_ms": info.solve_ms, "assemble_ms": info.assemble_ms,
+                "events": self.sim.last_info.n_events, "fallbacks": self.sim.last_info.n_exact_fallbacks,
+                "loop_ms": self.sim.last_info.loop_ms, "rate_ms": self.sim.last_info.rate_ms, "step_time": t}
+
+
+def bench_multi_gpu(args, metric: str, unit: str):
+    """bench.py --gpus N under torchrun: strong scaling of one KMC step on the same workload"""
+    import torch
+    import torch.distributed as dist
+    import bench
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    el, x, y, z, lat, nc, p = bench.workload(args.workload)
+    el = bench.substoichiometric(el, p)
+    s = SlabSim((el, x, y, z), p, rank, world, distributed_cg=not args.replicated_cg)
+    stats = []
+    for _ in range(args.warmup):
+        s.step(args.vd)
+    sampler = bench.ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = s.dev.ctx.launch_count()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        stats.append(s.step(args.vd))
+    e1.record(); e1.synchronize()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)          # device time, max over ranks
+    launches = s.dev.ctx.launch_count() - launches0
+    # e2e: host buffers in and out every step, on every rank
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        s.buf.sync_HostToGPU(s.dev)
+        s.step(args.vd)
+        s.buf.sync_GPUToHost(s.dev)
+    e1.record(); e1.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    # all ranks must hold the same state (replicated event loop on identical inputs)
+    chk = torch.tensor([float(s.buf.site_element.sum().item()), float(s.buf.site_charge.abs().sum().item())],
+                       dtype=torch.float64, device="cuda")
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    consistent = bool(torch.equal(lo, hi))
+    if rank == 0:
+        clocks = sampler.stop()
+        value = args.steps / (ms.item() * 1e-3)
+        med = lambda k: float(np.median([t[k] for t in stats]))
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms.item() / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "sites": s.dev.N, "nn": s.buf.nn_, "Vd": args.vd,
+                           "partition": f"x-slabs over {world} ranks: rows by nnz tiles (CG), targets by site (pairwise)",
+                           "cg": "distributed" if s.dcg is not None else "replicated",
+                           "l2": "inputs larger than L2"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": args.steps / (ms2.item() * 1e-3), "unit": unit, "h2d_bytes_per_step": s.buf.h2d_bytes(),
+                        "d2h_bytes_per_step": s.buf.d2h_bytes()},
+                "stage_ms": {"cg_solve": med("solve_ms"), "assemble": med("assemble_ms"), "rate_table": med("rate_ms"),
+                             "event_loop": med("loop_ms")},
+                "per_step": {"events": [t["events"] for t in stats], "cg_iterations": [t["cg_iterations"] for t in stats]},
+                "ranks_consistent": consistent, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()

@@ -194,6 +194,33 @@ int dkmc_ctx_set_exact_select(dkmc_ctx *ctx, int mode);
 /* device pointers of the last step's event tables (valid until the next step) */
 int dkmc_last_event_tables(dkmc_ctx *ctx, const int **d_event_type, const double **d_event_prob);
 
+/* ---- multi-GPU (no reference counterpart: the reference is single-GPU).
+ * One process per GPU.  The interior rows of K are split into contiguous ranges of whole SpMV
+ * tiles (an x-slab for x-major ordered sites); the PCG of a4/a5 then exchanges the halo of p
+ * with ncclSend/ncclRecv and all-reduces [p.Ap] and [r.D^-1 r, cluster sums] per iteration.
+ * Bootstrap: rank 0 calls dkmc_dist_unique_id, the host broadcasts the 128 bytes (e.g. through
+ * torch.distributed), every rank calls dkmc_dist_init. */
+#define DKMC_MAX_RANKS 64
+#define DKMC_MAX_HALO_SEGMENTS 64
+typedef struct {
+    int world;
+    int row_begin[DKMC_MAX_RANKS], row_end[DKMC_MAX_RANKS]; /* interior rows of every rank */
+    int n_send, n_recv;                                      /* this rank's halo segments [begin,end) */
+    int send_peer[DKMC_MAX_HALO_SEGMENTS], send_begin[DKMC_MAX_HALO_SEGMENTS], send_end[DKMC_MAX_HALO_SEGMENTS];
+    int recv_peer[DKMC_MAX_HALO_SEGMENTS], recv_begin[DKMC_MAX_HALO_SEGMENTS], recv_end[DKMC_MAX_HALO_SEGMENTS];
+} dkmc_dist_plan;
+int dkmc_spmv_tile_nnz(void); /* rows are assigned to SpMV tiles by row start, this many nnz per tile */
+int dkmc_dist_unique_id(char *id128);
+int dkmc_dist_init(dkmc_ctx *ctx, int rank, int world, const char *id128);
+int dkmc_dist_finalize(dkmc_ctx *ctx);
+/* background_potential_gpu_sparse (gpu_solvers.h:139-141) over `world` GPUs; on return every rank
+ * holds the full d_site_potential_boundary. */
+int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd,
+                                   double high_G, double low_G, const int *d_site_element,
+                                   const int *d_site_charge, const int *d_metals, int num_metals,
+                                   double *d_site_potential_boundary, const dkmc_dist_plan *plan,
+                                   const dkmc_solver_opts *opts, dkmc_solve_info *info);
+
 /* Measurement aid (no reference counterpart): achievable FP64 FMA throughput of this GPU in
  * TFLOP/s (8 independent DFMA chains per thread on every SM) — the roofline denominator of the
  * pairwise sum, which MEASURED_PEAKS.json does not carry. */
