@@ -183,8 +183,19 @@ __device__ __forceinline__ bool grid_sum_finish(double block_total, double *part
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
+    // fixed order (thread t adds partials t, t+B, t+2B, ...), loads issued eight at a time so the
+    // tail of the launch costs one or two L2 round trips instead of gridDim/blockDim of them
     double acc = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(partials + i);
+    const int n = (int)gridDim.x, B = (int)blockDim.x;
+    int i = threadIdx.x;
+    for (; i + 7 * B < n; i += 8 * B) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(partials + i + u * B);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; i < n; i += B) acc += __ldcg(partials + i);
     acc = block_sum(acc, sh);
     if (threadIdx.x == 0) {
         *result = acc;

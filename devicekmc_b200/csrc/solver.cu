@@ -14,6 +14,8 @@
 //     (uncharged-vacancy clusters coupled by high_G inside a low_G oxide) takes from plain CG.
 #include <nccl.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -25,6 +27,10 @@ constexpr int kSpmvTile = kSpmvCap - 64;    // nnz per tile by row start: with r
                                             // tile (+1 alignment slot) always fits one pass
 constexpr int kVecThreads = 256;
 constexpr int kMaxPartials = 1 << 16;
+
+// experiment switches (env DKMC_FLAGS): bit0 matrix loads cached (not streaming), bit1 streaming
+// vector traffic in the CG update, bit2 L2 persistence window on the matrix values
+static int g_flags = [] { const char *e = getenv("DKMC_FLAGS"); return e ? atoi(e) : 0; }();
 
 struct CgScalars {
     double rz, rz_new, pAp, alpha, beta, bb, stop, resnorm2, bnorm2;
@@ -85,17 +91,22 @@ __global__ void __launch_bounds__(128) assemble_kernel(
 }
 
 // ---------------------------------------------------------------- SpMV tiling
-__global__ void tile_rows_kernel(int m, int num_tiles, const int *__restrict__ row_ptr, int *__restrict__ tile_row) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > num_tiles) return;
-    if (t == num_tiles) { tile_row[t] = m; return; }
-    int target = t * kSpmvTile;
+__device__ __forceinline__ int first_row_at(const int *__restrict__ row_ptr, int m, long long target) {
     int lo = 0, hi = m;  // first r in [0,m) with row_ptr[r] >= target
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
         if (row_ptr[mid] >= target) hi = mid; else lo = mid + 1;
     }
-    tile_row[t] = lo;
+    return lo;
+}
+
+// tile t = rows whose first non-zero index lies in [t*T, (t+1)*T); info = (r0, r1, k0, k1)
+__global__ void tile_rows_kernel(int m, int num_tiles, const int *__restrict__ row_ptr, int4 *__restrict__ tile_info) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    int r0 = first_row_at(row_ptr, m, (long long)t * kSpmvTile);
+    int r1 = (t + 1 == num_tiles) ? m : first_row_at(row_ptr, m, (long long)(t + 1) * kSpmvTile);
+    tile_info[t] = make_int4(r0, r1, row_ptr[r0], row_ptr[r1]);
 }
 
 // y = A x over one nnz tile per block.  MODE 0: y only.  MODE 1: also dot(w, y) -> *dot_out.
@@ -106,16 +117,17 @@ __global__ void tile_rows_kernel(int m, int num_tiles, const int *__restrict__ r
 template <int MODE>
 __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(
     int m, int nnz, const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
-    const double *__restrict__ x, double *__restrict__ y, const int *__restrict__ tile_row,
+    const double *__restrict__ x, double *__restrict__ y, const int4 *__restrict__ tile_info,
     const double *__restrict__ w, const double *__restrict__ dinv, double *partials, unsigned int *counter,
-    double *dot_out, const int *done_flag) {
+    double *dot_out, const int *done_flag, int flags) {
     __shared__ __align__(16) double prod[kSpmvCap];
     __shared__ double red[32];
     if (done_flag && *done_flag) return;
-    const int r0 = tile_row[blockIdx.x], r1 = tile_row[blockIdx.x + 1];
+    const int4 ti = tile_info[blockIdx.x];
+    const int r0 = ti.x, r1 = ti.y;
     double local = 0.0;
     if (r0 < r1) {
-        const int k0 = row_ptr[r0], k1 = row_ptr[r1];
+        const int k0 = ti.z, k1 = ti.w;
         const int ka = k0 & ~1;  // even start: 16-byte aligned double2 / 8-byte aligned int2
         // row bounds of this thread's first row, requested before the big loads
         int my_r = r0 + threadIdx.x, ra = 0, rb = 0;
@@ -130,8 +142,13 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(
                 for (int u = 0; u < 4; ++u) {
                     int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
                     bool ok = k < k1;
-                    v[u] = ok ? __ldcs(val + k) : 0.0;
-                    c[u] = ok ? __ldcs(col + k) : 0;
+                    if (flags & 1) {  // keep the matrix in L2 across CG iterations
+                        v[u] = ok ? __ldg(val + k) : 0.0;
+                        c[u] = ok ? __ldg(col + k) : 0;
+                    } else {
+                        v[u] = ok ? __ldcs(val + k) : 0.0;
+                        c[u] = ok ? __ldcs(col + k) : 0;
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -171,15 +188,16 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(
 __global__ void __launch_bounds__(kSpmvThreads) residual_dd_kernel(
     int m, const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
     const double *__restrict__ x, const double *__restrict__ b, const double *__restrict__ dinv,
-    double *__restrict__ res, const int *__restrict__ tile_row, double *partials, unsigned int *counter,
+    double *__restrict__ res, const int4 *__restrict__ tile_info, double *partials, unsigned int *counter,
     double *res_out) {
     __shared__ double hi[kSpmvCap];
     __shared__ double lo[kSpmvCap];
     __shared__ double red[32];
-    const int r0 = tile_row[blockIdx.x], r1 = tile_row[blockIdx.x + 1];
+    const int4 ti = tile_info[blockIdx.x];
+    const int r0 = ti.x, r1 = ti.y;
     double local = 0.0;
     if (r0 < r1) {
-        const int k0 = row_ptr[r0], k1 = row_ptr[r1];
+        const int k0 = ti.z, k1 = ti.w;
         const int cnt = k1 - k0;
         const bool staged = cnt <= kSpmvCap;
         if (staged) {
@@ -459,6 +477,8 @@ __global__ void __launch_bounds__(kVecThreads) cg_init_kernel(int m, const doubl
     }
 }
 
+__device__ __forceinline__ double2 ld2s(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ void st2s(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
 __device__ __forceinline__ double2 ld2(const double *p, bool vec) {
     if (vec) return *reinterpret_cast<const double2 *>(p);
     return make_double2(p[0], p[1]);
@@ -475,20 +495,22 @@ __device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_c
 __global__ void __launch_bounds__(kVecThreads) cg_update_kernel(int m, double *x, const double *r_old,
                                                                double *r_new, const double *p,
                                                                const double *Ap, Precond P, double *partials,
-                                                               CgScalars *sc) {
+                                                               CgScalars *sc, int flags) {
     __shared__ double red[32];
     if (sc->done) return;
     const double alpha = sc->rz / sc->pAp;
     const bool vx = aligned16(x);
+    const bool stream = (flags & 2) != 0;
     double local = 0.0;
     const int n2 = (m + 1) >> 1;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += gridDim.x * blockDim.x) {
         const int i = 2 * j;
         if (i + 1 < m) {
-            double2 p2 = ld2(p + i, true), r2 = ld2(r_old + i, true), a2 = ld2(Ap + i, true), x2 = ld2(x + i, vx);
+            double2 p2 = ld2(p + i, true), r2 = stream ? ld2s(r_old + i) : ld2(r_old + i, true),
+                    a2 = stream ? ld2s(Ap + i) : ld2(Ap + i, true), x2 = (stream && vx) ? ld2s(x + i) : ld2(x + i, vx);
             x2.x += alpha * p2.x; x2.y += alpha * p2.y;
             r2.x -= alpha * a2.x; r2.y -= alpha * a2.y;
-            st2(x + i, x2, vx);
+            if (stream && vx) st2s(x + i, x2); else st2(x + i, x2, vx);
             st2(r_new + i, r2, true);
             local += r2.x * precond_apply_updated(P, i, r2.x, r_old, Ap, alpha);
             local += r2.y * precond_apply_updated(P, i + 1, r2.y, r_old, Ap, alpha);
@@ -559,7 +581,7 @@ __global__ void diag_inverse_kernel(int m, const int *__restrict__ row_ptr, cons
 }
 
 // ---------------------------------------------------------------- host side
-static int get_tiling(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int **tile_row, int *num_tiles) {
+static int get_tiling(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int4 **tile_row, int *num_tiles) {
     SpmvTiling &t = ctx->tiling;
     if (t.row_ptr != d_row_ptr || t.m != m || t.nnz != nnz) {
         if (t.d_tile_row) {
@@ -568,11 +590,12 @@ static int get_tiling(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const
             t.d_tile_row = nullptr;
         }
         t.num_tiles = ceil_div(nnz > 0 ? nnz : 1, kSpmvTile);
-        DKMC_CUDA(cudaMalloc(&t.d_tile_row, ((size_t)t.num_tiles + 1) * sizeof(int)));
-        DKMC_LAUNCH(ctx, tile_rows_kernel, ceil_div(t.num_tiles + 1, 256), 256, 0, m, t.num_tiles, d_row_ptr, t.d_tile_row);
+        DKMC_CUDA(cudaMalloc(&t.d_tile_row, ((size_t)t.num_tiles + 1) * sizeof(int4)));
+        DKMC_LAUNCH(ctx, tile_rows_kernel, ceil_div(t.num_tiles + 1, 256), 256, 0, m, t.num_tiles, d_row_ptr,
+                    reinterpret_cast<int4 *>(t.d_tile_row));
         t.row_ptr = d_row_ptr; t.m = m; t.nnz = nnz;
     }
-    *tile_row = t.d_tile_row;
+    *tile_row = reinterpret_cast<const int4 *>(t.d_tile_row);
     *num_tiles = t.num_tiles;
     return DKMC_OK;
 }
@@ -586,7 +609,7 @@ static int vec_grid(const dkmc_ctx *ctx, int m) {
 struct CgWork {
     double *r[2], *p, *Ap, *dinv, *res, *e, *partials;
     CgScalars *sc;
-    const int *tile_row;
+    const int4 *tile_row;
     int num_tiles;
     Precond P;
 };
@@ -647,7 +670,7 @@ static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const in
     const int vg = vec_grid(ctx, m);
     // r = b - A x, then z/p/rz/bb
     DKMC_LAUNCH(ctx, spmv_tile_kernel<2>, w.num_tiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, w.r[0],
-                w.tile_row, d_b, w.dinv, w.partials, &w.sc->cnt_c, &w.sc->resnorm2, (const int *)nullptr);
+                w.tile_row, d_b, w.dinv, w.partials, &w.sc->cnt_c, &w.sc->resnorm2, (const int *)nullptr, g_flags);
     DKMC_LAUNCH(ctx, cg_init_kernel, vg, kVecThreads, 0, m, w.r[0], d_b, w.P, w.p, tol, max_iter, w.partials, w.sc);
     CgScalars h;
     memset(&h, 0, sizeof(h));
@@ -657,9 +680,9 @@ static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const in
         for (int k = 0; k < check_every; ++k) {
             DKMC_LAUNCH(ctx, spmv_tile_kernel<1>, w.num_tiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, w.p,
                         w.Ap, w.tile_row, w.p, (const double *)nullptr, w.partials, &w.sc->cnt_c, &w.sc->pAp,
-                        &w.sc->done);
+                        &w.sc->done, g_flags);
             DKMC_LAUNCH(ctx, cg_update_kernel, vg, kVecThreads, 0, m, d_x, w.r[cur], w.r[cur ^ 1], w.p, w.Ap, w.P,
-                        w.partials, w.sc);
+                        w.partials, w.sc, g_flags);
             cur ^= 1;
             DKMC_LAUNCH(ctx, cg_direction_kernel, vg, kVecThreads, 0, m, w.r[cur], w.P, w.p, w.sc);
         }
@@ -938,7 +961,7 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
     if ((rc = halo_exchange(ctx, d, d_x))) return rc;
     if (nt > 0)
         DKMC_LAUNCH(ctx, spmv_tile_kernel<2>, nt, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, r,
-                    w.tile_row + d.t0, d_b, w.dinv, w.partials, &w.sc->cnt_c, &w.sc->resnorm2, (const int *)nullptr);
+                    w.tile_row + d.t0, d_b, w.dinv, w.partials, &w.sc->cnt_c, &w.sc->resnorm2, (const int *)nullptr, g_flags);
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.dinv, w.partials, &w.sc->cnt_a, d.red + 1);
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, d_b, w.dinv, w.partials, &w.sc->cnt_a, d.red + 2);
     if (n > 0) {
@@ -958,7 +981,7 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
             if (nt > 0)
                 DKMC_LAUNCH(ctx, spmv_tile_kernel<1>, nt, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap,
                             w.tile_row + d.t0, w.p, (const double *)nullptr, w.partials, &w.sc->cnt_c, d.red + 0,
-                            &w.sc->done);
+                            &w.sc->done, g_flags);
             else
                 DKMC_CUDA(cudaMemsetAsync(d.red, 0, sizeof(double), ctx->stream));
             DKMC_NCCL(ncclAllReduce(d.red, d.red, 1, ncclDouble, ncclSum, ds->comm, ctx->stream));
@@ -1043,12 +1066,12 @@ int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_
               const double *d_x, double *d_y) {
     DKMC_REQUIRE(ctx && d_row_ptr && d_col && d_val && d_x && d_y, "null pointer");
     DKMC_REQUIRE(m > 0 && nnz >= 0, "m, nnz");
-    const int *tile_row;
+    const int4 *tile_row;
     int num_tiles, rc;
     if ((rc = get_tiling(ctx, m, nnz, d_row_ptr, &tile_row, &num_tiles))) return rc;
     DKMC_LAUNCH(ctx, spmv_tile_kernel<0>, num_tiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, d_y, tile_row,
                 (const double *)nullptr, (const double *)nullptr, (double *)nullptr, (unsigned int *)nullptr,
-                (double *)nullptr, (const int *)nullptr);
+                (double *)nullptr, (const int *)nullptr, g_flags);
     return DKMC_OK;
 }
 
@@ -1121,6 +1144,24 @@ int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int
         if ((rc = build_clusters(ctx, m, NL, cls, sp->d_row_ptr, sp->d_col, val, &w))) return rc;
     }
     DKMC_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    if (g_flags & 4) {  // keep as much of the matrix as the persisting L2 carve-out holds
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->dev);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+        size_t bytes = (size_t)sp->nnz * sizeof(double);
+        if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = val;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = bytes > 0 ? (float)fmin(1.0, 0.9 * (double)max_persist / (double)bytes) : 0.f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        static bool once = false;
+        if (!once) { once = true; fprintf(stderr, "dkmc: L2 persist %d MB, window %zu MB, hitRatio %.2f\n", max_persist >> 20, bytes >> 20, attr.accessPolicyWindow.hitRatio); }
+    }
     // warm start: the interior of the previous potential (potential_solver_gpu.cu:754)
     double *x = d_site_potential_boundary + NL;
     rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info);

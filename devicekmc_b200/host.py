@@ -69,7 +69,7 @@ def write_xyz(filename: str, element, x, y, z, extra=None):
         f.write(f"{len(x)}\n\n")
         for i in range(len(x)):
             tail = "" if extra is None else "   " + "   ".join(repr(float(c[i])) for c in extra)
-            f.write(f"{return_element(element[i])}   {x[i]!r}   {y[i]!r}   {z[i]!r}{tail}\n")
+            f.write(f"{return_element(element[i])}   {float(x[i])!r}   {float(y[i])!r}   {float(z[i])!r}{tail}\n")
 
 
 class RandomNumberGenerator:
