@@ -149,7 +149,7 @@ void dkmc_default_solver_opts(dkmc_solver_opts *o) {
     o->check_every = 32;
     o->cluster_precond = 1;
     o->refine_tol = 1e-6;
-    o->est_tol = 1e-14;
+    o->est_tol = 1e-13;
 }
 
 }  // extern "C"

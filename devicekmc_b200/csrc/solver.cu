@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "scan.cuh"
+#include "spmv_tma.cuh"
 
 namespace dkmc {
 
@@ -551,6 +552,14 @@ __global__ void __launch_bounds__(kVecThreads) cg_direction_kernel(int m, const 
     }
 }
 
+// after a residual replacement: rz := r_true . M^-1 r_true decides convergence
+__global__ void replace_scalars_kernel(CgScalars *sc) {
+    if (threadIdx.x != 0) return;
+    if (sc->iters >= sc->max_iter) { sc->done = 1; return; }
+    sc->rz = sc->rz_new;
+    sc->done = (sc->rz_new <= sc->stop) ? 1 : 0;
+}
+
 // out = v . M^-1 v   (true-residual norm in the preconditioner's metric)
 __global__ void __launch_bounds__(kVecThreads) precond_norm_kernel(int m, const double *v, Precond P, double *partials,
                                                                   unsigned int *counter, double *out) {
@@ -663,30 +672,67 @@ static int build_clusters(dkmc_ctx *ctx, int m, int NL, const unsigned char *cls
     return DKMC_OK;
 }
 
+// SpMV over `ntiles` tiles starting at `tile_info`: the TMA-fed persistent kernel when the arrays
+// are 16-byte aligned (always true for our own allocations), else the register-staged one.
+template <int MODE>
+static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_row_ptr, const int *d_col,
+                       const double *d_val, const double *d_x, double *d_y, const int4 *tile_info, const double *w,
+                       const double *dinv, double *partials, unsigned int *counter, double *dot_out,
+                       const int *done_flag) {
+    if (ntiles <= 0) return DKMC_OK;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_val) | reinterpret_cast<uintptr_t>(d_col)) & 15) == 0;
+    if (aligned && !(g_flags & 16)) {
+        static bool configured = false;
+        if (!configured) {
+            DKMC_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+            configured = true;
+        }
+        int grid = ctx->num_sms * 3;
+        if (grid > ntiles) grid = ntiles;
+        DKMC_LAUNCH(ctx, spmv_tma_kernel<MODE>, grid, kTmaThreads, kTmaSmemBytes, ntiles, nnz, d_row_ptr, d_col, d_val, d_x,
+                    d_y, tile_info, w, dinv, partials, counter, dot_out, done_flag);
+    } else {
+        DKMC_LAUNCH(ctx, spmv_tile_kernel<MODE>, ntiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, d_y,
+                    tile_info, w, dinv, partials, counter, dot_out, done_flag, g_flags);
+    }
+    return DKMC_OK;
+}
+
 // Preconditioned CG on A x = b starting from x (in/out).  w.P must be set.
 static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                    const double *d_b, double *d_x, const CgWork &w, double tol, int max_iter, int check_every,
                    int *iters_out, int *converged, double *bb_out) {
     const int vg = vec_grid(ctx, m);
     // r = b - A x, then z/p/rz/bb
-    DKMC_LAUNCH(ctx, spmv_tile_kernel<2>, w.num_tiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, w.r[0],
-                w.tile_row, d_b, w.dinv, w.partials, &w.sc->cnt_c, &w.sc->resnorm2, (const int *)nullptr, g_flags);
+    int rc0;
+    if ((rc0 = launch_spmv<2>(ctx, w.num_tiles, m, nnz, d_row_ptr, d_col, d_val, d_x, w.r[0], w.tile_row, d_b, w.dinv,
+                              w.partials, &w.sc->cnt_c, &w.sc->resnorm2, nullptr))) return rc0;
     DKMC_LAUNCH(ctx, cg_init_kernel, vg, kVecThreads, 0, m, w.r[0], d_b, w.P, w.p, tol, max_iter, w.partials, w.sc);
     CgScalars h;
     memset(&h, 0, sizeof(h));
     int launched = 0, cur = 0;
+    const bool replace = (g_flags & 8) != 0;
     if (check_every < 1) check_every = 1;
     while (true) {
         for (int k = 0; k < check_every; ++k) {
-            DKMC_LAUNCH(ctx, spmv_tile_kernel<1>, w.num_tiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, w.p,
-                        w.Ap, w.tile_row, w.p, (const double *)nullptr, w.partials, &w.sc->cnt_c, &w.sc->pAp,
-                        &w.sc->done, g_flags);
+            if ((rc0 = launch_spmv<1>(ctx, w.num_tiles, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap, w.tile_row, w.p, nullptr,
+                                      w.partials, &w.sc->cnt_c, &w.sc->pAp, &w.sc->done))) return rc0;
             DKMC_LAUNCH(ctx, cg_update_kernel, vg, kVecThreads, 0, m, d_x, w.r[cur], w.r[cur ^ 1], w.p, w.Ap, w.P,
                         w.partials, w.sc, g_flags);
             cur ^= 1;
             DKMC_LAUNCH(ctx, cg_direction_kernel, vg, kVecThreads, 0, m, w.r[cur], w.P, w.p, w.sc);
         }
         launched += check_every;
+        if (replace) {
+            // residual replacement: swap the drifting recurrence residual for the true one
+            // (double-double), keep the search direction; convergence is then judged on the
+            // TRUE residual, so no restart is needed to reach rounding-level accuracy
+            DKMC_LAUNCH(ctx, residual_dd_kernel, w.num_tiles, kSpmvThreads, 0, m, d_row_ptr, d_col, d_val, d_x, d_b, w.dinv,
+                        w.r[cur], w.tile_row, w.partials, &w.sc->cnt_d, &w.sc->resnorm2);
+            DKMC_LAUNCH(ctx, precond_norm_kernel, vg, kVecThreads, 0, m, w.r[cur], w.P, w.partials, &w.sc->cnt_d,
+                        &w.sc->rz_new);
+            DKMC_LAUNCH(ctx, replace_scalars_kernel, 1, 32, 0, w.sc);
+        }
         DKMC_CUDA(cudaMemcpyAsync(&h, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
         DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (h.done || launched >= max_iter) break;
@@ -959,9 +1005,8 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
     double *r = w.r[0];
     int rc;
     if ((rc = halo_exchange(ctx, d, d_x))) return rc;
-    if (nt > 0)
-        DKMC_LAUNCH(ctx, spmv_tile_kernel<2>, nt, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, r,
-                    w.tile_row + d.t0, d_b, w.dinv, w.partials, &w.sc->cnt_c, &w.sc->resnorm2, (const int *)nullptr, g_flags);
+    if ((rc = launch_spmv<2>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, d_x, r, w.tile_row + d.t0, d_b, w.dinv, w.partials,
+                             &w.sc->cnt_c, &w.sc->resnorm2, nullptr))) return rc;
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.dinv, w.partials, &w.sc->cnt_a, d.red + 1);
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, d_b, w.dinv, w.partials, &w.sc->cnt_a, d.red + 2);
     if (n > 0) {
@@ -978,11 +1023,10 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
     while (true) {
         for (int k = 0; k < check_every; ++k) {
             if ((rc = halo_exchange(ctx, d, w.p))) return rc;
-            if (nt > 0)
-                DKMC_LAUNCH(ctx, spmv_tile_kernel<1>, nt, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap,
-                            w.tile_row + d.t0, w.p, (const double *)nullptr, w.partials, &w.sc->cnt_c, d.red + 0,
-                            &w.sc->done, g_flags);
-            else
+            if (nt > 0) {
+                if ((rc = launch_spmv<1>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap, w.tile_row + d.t0, w.p, nullptr,
+                                         w.partials, &w.sc->cnt_c, d.red + 0, &w.sc->done))) return rc;
+            } else
                 DKMC_CUDA(cudaMemsetAsync(d.red, 0, sizeof(double), ctx->stream));
             DKMC_NCCL(ncclAllReduce(d.red, d.red, 1, ncclDouble, ncclSum, ds->comm, ctx->stream));
             DKMC_LAUNCH(ctx, dist_update_kernel, vg, kVecThreads, 0, d.ra, d.rb, d_x, r, w.p, w.Ap, w.dinv, d.red + 0,
@@ -1069,10 +1113,8 @@ int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_
     const int4 *tile_row;
     int num_tiles, rc;
     if ((rc = get_tiling(ctx, m, nnz, d_row_ptr, &tile_row, &num_tiles))) return rc;
-    DKMC_LAUNCH(ctx, spmv_tile_kernel<0>, num_tiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, d_y, tile_row,
-                (const double *)nullptr, (const double *)nullptr, (double *)nullptr, (unsigned int *)nullptr,
-                (double *)nullptr, (const int *)nullptr, g_flags);
-    return DKMC_OK;
+    return launch_spmv<0>(ctx, num_tiles, m, nnz, d_row_ptr, d_col, d_val, d_x, d_y, tile_row, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, nullptr);
 }
 
 int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd, double high_G,

@@ -106,7 +106,7 @@ typedef struct {
     int cluster_precond; /* 1 (default): add one coarse unknown per uncharged-vacancy cluster to the
                             Jacobi preconditioner; 0: plain Jacobi as the reference */
     double refine_tol;   /* relative tolerance of each restart's correction solve (default 1e-6) */
-    double est_tol;      /* restart while max|M^-1 r_true| / max|x| exceeds this (default 1e-14) */
+    double est_tol;      /* restart while max|M^-1 r_true| / max|x| exceeds this (default 1e-13) */
 } dkmc_solver_opts;
 typedef struct {
     int iterations;        /* total CG iterations incl. refinement runs */
