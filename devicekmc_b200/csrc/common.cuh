@@ -50,7 +50,7 @@ enum Slot : int {
     S_SP_CNT, S_SCAN_BLOCK,
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
-    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED,
+    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR,
     S_LAST
 };
 static_assert(S_LAST <= kNumSlots, "increase kNumSlots");
@@ -60,6 +60,21 @@ struct SpmvTiling {
     int m = 0, nnz = 0;
     int num_tiles = 0;
     int *d_tile_row = nullptr;     // [num_tiles+1] first row of each nnz tile
+};
+
+// window-staged format of K for the CG's SpMV (spmv_win.cuh), built once per sparsity pattern
+struct WinFormat {
+    const int *row_ptr = nullptr, *col = nullptr;  // key
+    int m = 0, nnz = 0, num_tiles = 0;
+    bool ok = false;                     // every tile fits the format's limits
+    int fail_bits = 0, max_chunk = 0;
+    unsigned short *code_base = nullptr; // static: window position | diagonal bit
+    unsigned short *code = nullptr;      // per step: code_base | high_G bit
+    int *rp = nullptr;                   // padded row_ptr
+    double *diag = nullptr;              // per step: diagonal of K
+    void *hdr = nullptr, *runs = nullptr;
+    const double *val_tag = nullptr;     // the assembled CSR values `code`/`diag` correspond to
+    double m_high = 0.0, m_low = 0.0;    // -high_G, -low_G
 };
 
 }  // namespace dkmc
@@ -81,6 +96,7 @@ struct dkmc_ctx {
         bool valid = false;
     } grid;
     dkmc::SpmvTiling tiling;
+    dkmc::WinFormat win;
     // event loop state for dkmc_kmc_step_continue
     struct {
         int N = 0, nn = 0;
@@ -96,9 +112,21 @@ struct dkmc_ctx {
     int exact_select = 0;
     void *dist = nullptr;  // DistState (NCCL communicator) when running slab-partitioned
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    // side stream: the pairwise sum (FP64-bound) runs there while the CG (HBM-bound) runs on `stream`
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_pw0 = nullptr, ev_pw1 = nullptr;
+    struct {
+        bool active = false;
+        int pbc = 0, N = 0, row_begin = 0, row_end = 0;
+        const int *d_charge = nullptr;
+        double *d_out = nullptr;
+    } pw_pending;
+    int pw_side_blocks_per_sm = 6;   // residency of the pairwise kernel while it shares the SMs with the CG
 };
 
 namespace dkmc {
+
+void free_win_format(dkmc_ctx *ctx);
 
 // returns a device buffer of at least `bytes` for `slot` (contents NOT preserved on growth)
 int ensure_slot(dkmc_ctx *ctx, int slot, size_t bytes, void **out);
@@ -113,9 +141,31 @@ inline int ensure(dkmc_ctx *ctx, int slot, size_t count, T **out) {
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-#define DKMC_LAUNCH(ctx, kernel, grid, block, smem, ...)                                      \
+#define DKMC_LAUNCH(ctx, kernel, grid, block, smem, ...) \
+    DKMC_LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, smem, __VA_ARGS__)
+
+// Files whose kernels run while the pairwise sum shares the SMs with the CG define
+// DKMC_CARVEOUT_MAXSHARED: the L1/shared split of an SM cannot change while CTAs are resident, so
+// every kernel of that window asks for the same (largest shared memory) carve-out — otherwise a
+// CTA that needs another split waits until the SM has drained.
+#ifdef DKMC_CARVEOUT_MAXSHARED
+#define DKMC_SET_CARVEOUT(kernel)                                                             \
     do {                                                                                      \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
+        static bool cfg__ = false;                                                            \
+        if (!cfg__) {                                                                         \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,      \
+                                 (int)cudaSharedmemCarveoutMaxShared);                        \
+            cfg__ = true;                                                                     \
+        }                                                                                     \
+    } while (0)
+#else
+#define DKMC_SET_CARVEOUT(kernel) do { } while (0)
+#endif
+
+#define DKMC_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                             \
+    do {                                                                                      \
+        DKMC_SET_CARVEOUT(kernel);                                                            \
+        kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                             \
         (ctx)->launches++;                                                                    \
         cudaError_t err__ = cudaPeekAtLastError();                                            \
         if (err__ != cudaSuccess) {                                                           \

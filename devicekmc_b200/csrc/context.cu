@@ -1,6 +1,8 @@
 // devicekmc-b200 — context, error text, device selection (C-ABI plumbing).
 // Replaces get_gpu_info / set_gpu (kmc_events.cu:15-32) and the per-call cudaMalloc/cudaFree
 // churn of the reference (potential_solver_gpu.cu:397-493,735-779) with a persistent arena.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dkmc {
@@ -12,6 +14,14 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+void free_win_format(dkmc_ctx *ctx) {
+    WinFormat &w = ctx->win;
+    void *ptrs[6] = {w.code_base, w.code, w.rp, w.diag, w.hdr, w.runs};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    w = WinFormat();
 }
 
 int ensure_slot(dkmc_ctx *ctx, int slot, size_t bytes, void **out) {
@@ -82,6 +92,11 @@ int dkmc_ctx_create(dkmc_ctx **out) {
     DKMC_CUDA(cudaEventCreate(&ctx->ev_a));
     DKMC_CUDA(cudaEventCreate(&ctx->ev_b));
     DKMC_CUDA(cudaEventCreate(&ctx->ev_c));
+    DKMC_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    DKMC_CUDA(cudaEventCreate(&ctx->ev_pw0));
+    DKMC_CUDA(cudaEventCreate(&ctx->ev_pw1));
+    if (const char *e = getenv("DKMC_PW_SIDE_BPS")) { int v = atoi(e); if (v > 0) ctx->pw_side_blocks_per_sm = v; }
     *out = ctx;
     return DKMC_OK;
 }
@@ -89,9 +104,14 @@ int dkmc_ctx_create(dkmc_ctx **out) {
 int dkmc_ctx_destroy(dkmc_ctx *ctx) {
     if (!ctx) return DKMC_OK;
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_pw0) cudaEventDestroy(ctx->ev_pw0);
+    if (ctx->ev_pw1) cudaEventDestroy(ctx->ev_pw1);
     for (int s = 0; s < kNumSlots; ++s)
         if (ctx->slot_ptr[s]) cudaFree(ctx->slot_ptr[s]);
     if (ctx->tiling.d_tile_row) cudaFree(ctx->tiling.d_tile_row);
+    free_win_format(ctx);
     if (ctx->d_layerE) cudaFree(ctx->d_layerE);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);

@@ -7,6 +7,7 @@
 // compacted (ascending j = the CPU summation order), tiles of them are staged in shared memory
 // and every thread owns one target site and accumulates in registers — no atomics, FP64-pipe
 // bound, O(N * N_charged).
+#define DKMC_CARVEOUT_MAXSHARED 1
 #include "common.cuh"
 #include "scan.cuh"
 #include "erfc_coeffs.cuh"
@@ -16,6 +17,7 @@ namespace dkmc {
 constexpr int kPwThreads = 128;
 constexpr int kPwTile = 256;       // charged sources per shared-memory tile
 constexpr int kCompactBlock = 1024;
+constexpr int kPwFullBlocksPerSm = 10;  // 48 registers x 128 threads: ten CTAs fill an SM
 
 struct __align__(32) ChargedSite { double x, y, z, q; };
 
@@ -108,56 +110,111 @@ __device__ __forceinline__ double erfc_fast(double t) {
 
 // phi_c[i] = k q_e sum_j q_j erfc(r_ij / (sigma sqrt 2)) / r_ij.  One target per thread, sources
 // staged in shared memory, two independent sources per iteration for ILP, no atomics.
+// Persistent CTAs: each fetches tiles of kPwThreads targets from an atomic counter, so the launch
+// can be sized to a chosen residency per SM (the whole SM when the sum runs alone, a share of it
+// when it runs beside the CG on the side stream).  Every target's sum runs over the compacted
+// sources in ascending site order, so the result does not depend on the tile schedule.
 template <bool PBC>
 __global__ void __launch_bounds__(kPwThreads) pairwise_kernel(
     int row_begin, int row_end, const double *__restrict__ x, const double *__restrict__ y,
     const double *__restrict__ z, const int *__restrict__ n_src_ptr, const ChargedSite *__restrict__ src,
     const int *__restrict__ src_idx, const double *__restrict__ lattice, const double *__restrict__ sigma_ptr,
-    const double *__restrict__ k_ptr, double *__restrict__ out) {
+    const double *__restrict__ k_ptr, int *tile_counter, double *__restrict__ out) {
     __shared__ ChargedSite tile[kPwTile];
     __shared__ int tile_idx[kPwTile];
-    const int i = row_begin + blockIdx.x * kPwThreads + threadIdx.x;
-    const bool valid = i < row_end;
-    const double xi = valid ? x[i] : 0.0, yi = valid ? y[i] : 0.0, zi = valid ? z[i] : 0.0;
+    __shared__ int s_tile;
     const int nsrc = *n_src_ptr;
     const double sigma = *sigma_ptr, kc = *k_ptr;
     const double ly = lattice[1], lz = lattice[2];
     const double inv_ly = 1.0 / ly, inv_lz = 1.0 / lz;
     const double cscale = 1e-10 / (sigma * sqrt(2.0));  // t = r[Angstrom] * cscale
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    double acc0 = 0.0, acc1 = 0.0;
+    const int n_tiles = (row_end - row_begin + kPwThreads - 1) / kPwThreads;
 
-    auto pair_term = [&](const ChargedSite &s, int sidx) -> double {
-        double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
-        if (PBC) {
-            dy = fma(-rint(dy * inv_ly), ly, dy);
-            dz = fma(-rint(dz * inv_lz), lz, dz);
-        }
-        double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        double rinv = rsqrt_fast(r2);
-        double r = r2 * rinv;
-        double term = s.q * erfc_fast(r * cscale) * rinv;
-        term = (r2 == 0.0) ? s.q * inf : term;   // coincident sites: the reference divides by zero
-        return (sidx == i) ? 0.0 : term;         // i != j (potential_solver.cpp:422)
-    };
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int tile_id = s_tile;
+        if (tile_id >= n_tiles) break;
+        const int i = row_begin + tile_id * kPwThreads + threadIdx.x;
+        const bool valid = i < row_end;
+        const double xi = valid ? x[i] : 0.0, yi = valid ? y[i] : 0.0, zi = valid ? z[i] : 0.0;
+        double acc0 = 0.0, acc1 = 0.0;
 
-    for (int t0 = 0; t0 < nsrc; t0 += kPwTile) {
-        const int nt = min(kPwTile, nsrc - t0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < nt; t += kPwThreads) {
-            tile[t] = src[t0 + t];
-            tile_idx[t] = src_idx[t0 + t];
+        auto pair_term = [&](const ChargedSite &s, int sidx) -> double {
+            double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
+            if (PBC) {
+                dy = fma(-rint(dy * inv_ly), ly, dy);
+                dz = fma(-rint(dz * inv_lz), lz, dz);
+            }
+            double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            double rinv = rsqrt_fast(r2);
+            double r = r2 * rinv;
+            double term = s.q * erfc_fast(r * cscale) * rinv;
+            term = (r2 == 0.0) ? s.q * inf : term;   // coincident sites: the reference divides by zero
+            return (sidx == i) ? 0.0 : term;         // i != j (potential_solver.cpp:422)
+        };
+
+        for (int t0 = 0; t0 < nsrc; t0 += kPwTile) {
+            const int nt = min(kPwTile, nsrc - t0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < nt; t += kPwThreads) {
+                tile[t] = src[t0 + t];
+                tile_idx[t] = src_idx[t0 + t];
+            }
+            __syncthreads();
+            int t = 0;
+            for (; t + 1 < nt; t += 2) {
+                acc0 += pair_term(tile[t], tile_idx[t]);
+                acc1 += pair_term(tile[t + 1], tile_idx[t + 1]);
+            }
+            if (t < nt) acc0 += pair_term(tile[t], tile_idx[t]);
         }
-        __syncthreads();
-        int t = 0;
-        for (; t + 1 < nt; t += 2) {
-            acc0 += pair_term(tile[t], tile_idx[t]);
-            acc1 += pair_term(tile[t + 1], tile_idx[t + 1]);
-        }
-        if (t < nt) acc0 += pair_term(tile[t], tile_idx[t]);
+        // rinv is in 1/Angstrom: 1e10 converts to 1/m
+        if (valid) out[i] = (acc0 + acc1) * (kc * kElementaryCharge * 1e10);
     }
-    // rinv is in 1/Angstrom: 1e10 converts to 1/m
-    if (valid) out[i] = (acc0 + acc1) * (kc * kElementaryCharge * 1e10);
+}
+
+// compaction of the charged sites (on the context's main stream) and the tile counter
+static int pairwise_prepare(dkmc_ctx *ctx, int N, const double *d_x, const double *d_y, const double *d_z,
+                            const int *d_site_charge, ChargedSite **src_out, int **src_idx_out, int **total_out,
+                            int **tile_counter_out) {
+    const int nb = ceil_div(N, kCompactBlock);
+    int *counts, *tmp, *src_idx, *tile_counter;
+    ChargedSite *src;
+    int rc;
+    // counts | inclusive | total
+    if ((rc = ensure<int>(ctx, S_PW_COUNT, (size_t)2 * nb + 4, &counts))) return rc;
+    if ((rc = ensure<int>(ctx, S_SCAN_BLOCK, (size_t)ceil_div(nb, kScanTile) + 1, &tmp))) return rc;
+    if ((rc = ensure<ChargedSite>(ctx, S_PW_SRC, (size_t)N, &src))) return rc;
+    if ((rc = ensure<int>(ctx, S_PW_FLAGS, (size_t)N, &src_idx))) return rc;
+    if ((rc = ensure<int>(ctx, S_PW_TILECTR, 4, &tile_counter))) return rc;
+    int *incl = counts + nb, *total = counts + 2 * nb;
+    DKMC_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), ctx->stream));
+    DKMC_LAUNCH(ctx, charged_count_kernel, nb, kCompactBlock, 0, N, d_site_charge, counts);
+    if ((rc = inclusive_scan<int>(ctx, counts, nb, incl, tmp))) return rc;
+    DKMC_LAUNCH(ctx, charged_scatter_kernel, nb, kCompactBlock, 0, N, nb, d_site_charge, d_x, d_y, d_z, counts, incl,
+                src, src_idx, total);
+    *src_out = src; *src_idx_out = src_idx; *total_out = total; *tile_counter_out = tile_counter;
+    return DKMC_OK;
+}
+
+static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm, int pbc, int row_begin, int row_end,
+                           const double *d_lattice, const double *d_sigma, const double *d_k, const double *d_x,
+                           const double *d_y, const double *d_z, const ChargedSite *src, const int *src_idx,
+                           const int *total, int *tile_counter, double *d_out) {
+    const int tiles = ceil_div(row_end - row_begin, kPwThreads);
+    int grid = ctx->num_sms * blocks_per_sm;
+    if (grid > tiles) grid = tiles;
+    if (pbc) {
+        DKMC_LAUNCH_ON(ctx, stream, pairwise_kernel<true>, grid, kPwThreads, 0, row_begin, row_end, d_x, d_y, d_z, total,
+                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, d_out);
+    } else {
+        DKMC_LAUNCH_ON(ctx, stream, pairwise_kernel<false>, grid, kPwThreads, 0, row_begin, row_end, d_x, d_y, d_z, total,
+                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, d_out);
+    }
+    return DKMC_OK;
 }
 
 }  // namespace dkmc
@@ -166,6 +223,48 @@ using namespace dkmc;
 
 extern "C" {
 
+int dkmc_poisson_gridless_begin(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice, const double *d_sigma,
+                                const double *d_k, const double *d_x, const double *d_y, const double *d_z,
+                                const int *d_site_charge, int row_begin, int row_end,
+                                double *d_site_potential_charge) {
+    DKMC_REQUIRE(ctx && d_lattice && d_sigma && d_k && d_x && d_y && d_z && d_site_charge && d_site_potential_charge,
+                 "null pointer");
+    DKMC_REQUIRE(N > 0 && row_begin >= 0 && row_end <= N && row_begin <= row_end, "row range");
+    DKMC_REQUIRE(!ctx->pw_pending.active, "a pairwise sum is already in flight: call dkmc_poisson_gridless_join");
+    ChargedSite *src;
+    int *src_idx, *total, *tile_counter;
+    int rc;
+    if ((rc = pairwise_prepare(ctx, N, d_x, d_y, d_z, d_site_charge, &src, &src_idx, &total, &tile_counter))) return rc;
+    // fork: the side stream starts after the compaction and everything issued before it
+    DKMC_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    DKMC_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    DKMC_CUDA(cudaEventRecord(ctx->ev_pw0, ctx->side_stream));
+    if (row_end > row_begin)
+        if ((rc = pairwise_launch(ctx, ctx->side_stream, ctx->pw_side_blocks_per_sm, pbc, row_begin, row_end, d_lattice,
+                                  d_sigma, d_k, d_x, d_y, d_z, src, src_idx, total, tile_counter,
+                                  d_site_potential_charge))) return rc;
+    DKMC_CUDA(cudaEventRecord(ctx->ev_pw1, ctx->side_stream));
+    auto &pp = ctx->pw_pending;
+    pp.active = true; pp.pbc = pbc; pp.N = N; pp.row_begin = row_begin; pp.row_end = row_end;
+    pp.d_charge = d_site_charge; pp.d_out = d_site_potential_charge;
+    return DKMC_OK;
+}
+
+int dkmc_poisson_gridless_join(dkmc_ctx *ctx, double *pairwise_ms) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    if (pairwise_ms) *pairwise_ms = 0.0;
+    if (!ctx->pw_pending.active) return DKMC_OK;
+    ctx->pw_pending.active = false;
+    DKMC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pw1, 0));  // later work on the main stream sees the result
+    DKMC_CUDA(cudaEventSynchronize(ctx->ev_pw1));
+    if (pairwise_ms) {
+        float ms = 0.f;
+        DKMC_CUDA(cudaEventElapsedTime(&ms, ctx->ev_pw0, ctx->ev_pw1));
+        *pairwise_ms = ms;
+    }
+    return DKMC_OK;
+}
+
 int dkmc_poisson_gridless_rows(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice, const double *d_sigma,
                                const double *d_k, const double *d_x, const double *d_y, const double *d_z,
                                const int *d_site_charge, int row_begin, int row_end,
@@ -173,29 +272,21 @@ int dkmc_poisson_gridless_rows(dkmc_ctx *ctx, int pbc, int N, const double *d_la
     DKMC_REQUIRE(ctx && d_lattice && d_sigma && d_k && d_x && d_y && d_z && d_site_charge && d_site_potential_charge,
                  "null pointer");
     DKMC_REQUIRE(N > 0 && row_begin >= 0 && row_end <= N && row_begin <= row_end, "row range");
-    if (row_begin == row_end) return DKMC_OK;
-    const int nb = ceil_div(N, kCompactBlock);
-    int *counts, *tmp, *src_idx;
-    ChargedSite *src;
-    int rc;
-    // counts | inclusive | total
-    if ((rc = ensure<int>(ctx, S_PW_COUNT, (size_t)2 * nb + 4, &counts))) return rc;
-    if ((rc = ensure<int>(ctx, S_SCAN_BLOCK, (size_t)ceil_div(nb, kScanTile) + 1, &tmp))) return rc;
-    if ((rc = ensure<ChargedSite>(ctx, S_PW_SRC, (size_t)N, &src))) return rc;
-    if ((rc = ensure<int>(ctx, S_PW_FLAGS, (size_t)N, &src_idx))) return rc;
-    int *incl = counts + nb, *total = counts + 2 * nb;
-    DKMC_LAUNCH(ctx, charged_count_kernel, nb, kCompactBlock, 0, N, d_site_charge, counts);
-    if ((rc = inclusive_scan<int>(ctx, counts, nb, incl, tmp))) return rc;
-    DKMC_LAUNCH(ctx, charged_scatter_kernel, nb, kCompactBlock, 0, N, nb, d_site_charge, d_x, d_y, d_z, counts, incl,
-                src, src_idx, total);
-    const int rows = row_end - row_begin;
-    if (pbc) {
-        DKMC_LAUNCH(ctx, pairwise_kernel<true>, ceil_div(rows, kPwThreads), kPwThreads, 0, row_begin, row_end, d_x, d_y,
-                    d_z, total, src, src_idx, d_lattice, d_sigma, d_k, d_site_potential_charge);
-    } else {
-        DKMC_LAUNCH(ctx, pairwise_kernel<false>, ceil_div(rows, kPwThreads), kPwThreads, 0, row_begin, row_end, d_x, d_y,
-                    d_z, total, src, src_idx, d_lattice, d_sigma, d_k, d_site_potential_charge);
+    auto &pp = ctx->pw_pending;
+    if (pp.active) {
+        // the same sum was started ahead of time (dkmc_poisson_gridless_begin): just join it
+        const bool same = pp.pbc == pbc && pp.N == N && pp.row_begin == row_begin && pp.row_end == row_end &&
+                          pp.d_charge == d_site_charge && pp.d_out == d_site_potential_charge;
+        int rc = dkmc_poisson_gridless_join(ctx, nullptr);
+        if (rc || same) return rc;
     }
+    if (row_begin == row_end) return DKMC_OK;
+    ChargedSite *src;
+    int *src_idx, *total, *tile_counter;
+    int rc;
+    if ((rc = pairwise_prepare(ctx, N, d_x, d_y, d_z, d_site_charge, &src, &src_idx, &total, &tile_counter))) return rc;
+    if ((rc = pairwise_launch(ctx, ctx->stream, kPwFullBlocksPerSm, pbc, row_begin, row_end, d_lattice, d_sigma, d_k, d_x,
+                              d_y, d_z, src, src_idx, total, tile_counter, d_site_potential_charge))) return rc;
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
     return DKMC_OK;
 }
@@ -205,6 +296,12 @@ int dkmc_poisson_gridless(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice
                           const int *d_site_charge, double *d_site_potential_charge) {
     return dkmc_poisson_gridless_rows(ctx, pbc, N, d_lattice, d_sigma, d_k, d_x, d_y, d_z, d_site_charge, 0, N,
                                       d_site_potential_charge);
+}
+
+int dkmc_ctx_set_pairwise_share(dkmc_ctx *ctx, int blocks_per_sm) {
+    DKMC_REQUIRE(ctx != nullptr && blocks_per_sm >= 1 && blocks_per_sm <= 16, "blocks_per_sm in 1..16");
+    ctx->pw_side_blocks_per_sm = blocks_per_sm;
+    return DKMC_OK;
 }
 
 }  // extern "C"

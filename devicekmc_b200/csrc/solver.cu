@@ -16,9 +16,11 @@
 
 #include <cstdlib>
 
+#define DKMC_CARVEOUT_MAXSHARED 1
 #include "common.cuh"
 #include "scan.cuh"
 #include "spmv_tma.cuh"
+#include "spmv_win.cuh"
 
 namespace dkmc {
 
@@ -61,7 +63,8 @@ __global__ void __launch_bounds__(128) assemble_kernel(
     const unsigned char *__restrict__ cls, const int *__restrict__ row_ptr, const int *__restrict__ col,
     const int *__restrict__ lrp, const int *__restrict__ lcol, const int *__restrict__ rrp,
     const int *__restrict__ rcol, double *__restrict__ val, double *__restrict__ rhs,
-    double *__restrict__ dinv) {
+    double *__restrict__ dinv, const unsigned short *__restrict__ code_base, unsigned short *__restrict__ code,
+    double *__restrict__ diag_out) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     const double VL = -Vd / 2, VR = Vd / 2;
@@ -77,8 +80,10 @@ __global__ void __launch_bounds__(128) assemble_kernel(
     for (int p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
         int c = col[p];
         if (c == r) { diag_pos = p; continue; }
-        double G = conductance(ci, cls[c + NL], high_G, low_G);
+        const unsigned char cj = cls[c + NL];
+        double G = conductance(ci, cj, high_G, low_G);
         val[p] = -G;
+        if (code) code[p] = code_base[p] | ((ci != 0 && ci == cj) ? 0x4000 : 0);  // window-staged format: high_G bit
         diag = __dadd_rn(diag, G);
     }
     for (int p = rrp[r]; p < rrp[r + 1]; ++p) {
@@ -86,7 +91,11 @@ __global__ void __launch_bounds__(128) assemble_kernel(
         diag = __dadd_rn(diag, G);
         ksub = __dadd_rn(ksub, __dmul_rn(-G, VR));
     }
-    if (diag_pos >= 0) val[diag_pos] = diag;
+    if (diag_pos >= 0) {
+        val[diag_pos] = diag;
+        if (code) code[diag_pos] = code_base[diag_pos];
+    }
+    if (diag_out) diag_out[r] = diag;
     rhs[r] = -ksub;  // D*phi = -Ksub (potential_solver.cpp:379,396)
     if (dinv) dinv[r] = 1.0 / diag;
 }
@@ -296,6 +305,7 @@ __global__ void cluster_mark_kernel(int m, int NL, const unsigned char *__restri
 }
 
 constexpr int kCompactThreads = 1024;
+constexpr int kClusterThreads = 512;   // one CTA; small enough to fit beside the overlapped pairwise kernel
 
 __global__ void __launch_bounds__(kCompactThreads) flag_count_kernel(int n, const int *__restrict__ flag,
                                                                     int *__restrict__ block_count) {
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(kCompactThreads) flag_scatter_kernel(int n, in
 
 // One CTA: connected components of the clustered rows (min-label propagation with pointer
 // jumping), bitonic sort of (label, position) keys, cluster segments, row -> sorted position.
-__global__ void __launch_bounds__(1024) cluster_build_kernel(int NL, const unsigned char *__restrict__ cls,
+__global__ void __launch_bounds__(kClusterThreads) cluster_build_kernel(int NL, const unsigned char *__restrict__ cls,
                                                              const int *__restrict__ row_ptr,
                                                              const int *__restrict__ col, const int *n_cl_ptr,
                                                              const int *list, int *pos, int *lab,
@@ -665,21 +675,82 @@ static int build_clusters(dkmc_ctx *ctx, int m, int NL, const unsigned char *cls
     DKMC_LAUNCH(ctx, flag_count_kernel, nb, kCompactThreads, 0, m, flag, bcount);
     if ((rc = inclusive_scan<int>(ctx, bcount, nb, bincl, tmp))) return rc;
     DKMC_LAUNCH(ctx, flag_scatter_kernel, nb, kCompactThreads, 0, m, nb, flag, bcount, bincl, list, pos, total);
-    DKMC_LAUNCH(ctx, cluster_build_kernel, 1, 1024, 0, NL, cls, d_row_ptr, d_col, total, list, pos, lab, keys, mem_row,
+    DKMC_LAUNCH(ctx, cluster_build_kernel, 1, kClusterThreads, 0, NL, cls, d_row_ptr, d_col, total, list, pos, lab, keys, mem_row,
                 seg_start, seg_len);
     DKMC_LAUNCH(ctx, cluster_weight_kernel, 64, 128, 0, total, pos, seg_start, seg_len, mem_row, d_row_ptr, d_col, d_val, wts);
     w->P = Precond{w->dinv, pos, seg_start, seg_len, mem_row, wts};
     return DKMC_OK;
 }
 
-// SpMV over `ntiles` tiles starting at `tile_info`: the TMA-fed persistent kernel when the arrays
-// are 16-byte aligned (always true for our own allocations), else the register-staged one.
+// Builds (once per sparsity pattern) the window-staged format of spmv_win.cuh.
+static int get_win_format(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const int4 *tile_info,
+                          int num_tiles) {
+    WinFormat &w = ctx->win;
+    if (w.row_ptr == d_row_ptr && w.col == d_col && w.m == m && w.nnz == nnz) return DKMC_OK;
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_win_format(ctx);
+    const int rp_pad = ((m + 1 + 3) & ~3) + 8;
+    DKMC_CUDA(cudaMalloc(&w.code_base, ((size_t)nnz + 32) * sizeof(unsigned short)));
+    DKMC_CUDA(cudaMalloc(&w.code, ((size_t)nnz + 32) * sizeof(unsigned short)));
+    DKMC_CUDA(cudaMalloc(&w.rp, (size_t)rp_pad * sizeof(int)));
+    DKMC_CUDA(cudaMalloc(&w.diag, ((size_t)m + 8) * sizeof(double)));
+    DKMC_CUDA(cudaMalloc(&w.hdr, (size_t)num_tiles * sizeof(WinTileHdr)));
+    DKMC_CUDA(cudaMalloc(&w.runs, (size_t)num_tiles * kWinMaxRuns * sizeof(int2)));
+    DKMC_CUDA(cudaMemsetAsync(w.code_base, 0, ((size_t)nnz + 32) * sizeof(unsigned short), ctx->stream));
+    DKMC_CUDA(cudaMemsetAsync(w.code, 0, ((size_t)nnz + 32) * sizeof(unsigned short), ctx->stream));
+    DKMC_CUDA(cudaMemsetAsync(w.diag, 0, ((size_t)m + 8) * sizeof(double), ctx->stream));
+    int *flags;  // fail bits | max chunk
+    int rc;
+    if ((rc = ensure<int>(ctx, S_SEL_OUT, 4, &flags))) return rc;
+    DKMC_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
+    DKMC_LAUNCH(ctx, win_copy_rowptr_kernel, ceil_div(rp_pad, 256), 256, 0, m, rp_pad, d_row_ptr, w.rp);
+    DKMC_LAUNCH(ctx, win_build_kernel, num_tiles, 256, 0, m, num_tiles, d_row_ptr, d_col, tile_info, w.code_base,
+                static_cast<WinTileHdr *>(w.hdr), static_cast<int2 *>(w.runs), flags, flags + 1);
+    int h[2] = {0, 0};
+    DKMC_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    w.row_ptr = d_row_ptr; w.col = d_col; w.m = m; w.nnz = nnz; w.num_tiles = num_tiles;
+    w.fail_bits = h[0]; w.max_chunk = h[1];
+    w.ok = (h[0] == 0) && !(g_flags & 32);
+    w.val_tag = nullptr;
+    if (getenv("DKMC_VERBOSE"))
+        fprintf(stderr, "dkmc: window-staged SpMV format: %d tiles, largest staged tile %d bytes, fail bits %d -> %s\n",
+                num_tiles, h[1], h[0], w.ok ? "enabled" : "CSR kernels");
+    return DKMC_OK;
+}
+
+// SpMV over `ntiles` tiles starting at `tile_info`.  Three kernels, fastest applicable first:
+//   * window-staged (spmv_win.cuh) when d_val is the matrix the context assembled last and x can be
+//     bulk-copied (64-byte aligned, readable up to the next multiple of 8 entries);
+//   * TMA-fed CSR (spmv_tma.cuh) when val/col are 16-byte aligned;
+//   * register-staged CSR otherwise.
+// All three produce bit-identical y.  x_readable = number of doubles that may be read from d_x.
 template <int MODE>
 static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_row_ptr, const int *d_col,
                        const double *d_val, const double *d_x, double *d_y, const int4 *tile_info, const double *w,
                        const double *dinv, double *partials, unsigned int *counter, double *dot_out,
-                       const int *done_flag) {
+                       const int *done_flag, int x_readable = 0) {
     if (ntiles <= 0) return DKMC_OK;
+    const WinFormat &wf = ctx->win;
+    if (wf.ok && wf.row_ptr == d_row_ptr && wf.val_tag == d_val && d_val != nullptr &&
+        (reinterpret_cast<uintptr_t>(d_x) & 63) == 0 && x_readable >= ((m + 7) & ~7) && (MODE != 1 || w == d_x)) {
+        static bool configured = false;
+        if (!configured) {
+            DKMC_CUDA(cudaFuncSetAttribute(spmv_win_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemBytes));
+            configured = true;
+        }
+        const int t0 = (int)(tile_info - reinterpret_cast<const int4 *>(ctx->tiling.d_tile_row));
+        WinMatrix A;
+        A.code = wf.code; A.rp = wf.rp; A.diag = wf.diag;
+        A.hdr = static_cast<const WinTileHdr *>(wf.hdr) + t0;
+        A.runs = static_cast<const int2 *>(wf.runs) + (size_t)t0 * kWinMaxRuns;
+        A.m_high = wf.m_high; A.m_low = wf.m_low; A.num_tiles = ntiles;
+        int grid = ctx->num_sms < ntiles ? ctx->num_sms : ntiles;
+        static const int dbg = [] { const char *e = getenv("DKMC_WIN_DBG"); return e ? atoi(e) : 0; }();
+        DKMC_LAUNCH(ctx, spmv_win_kernel<MODE>, grid, kWinThreads, kWinSmemBytes, A, d_x, d_y, w, dinv, partials, counter,
+                    dot_out, done_flag, dbg);
+        return DKMC_OK;
+    }
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_val) | reinterpret_cast<uintptr_t>(d_col)) & 15) == 0;
     if (aligned && !(g_flags & 16)) {
         static bool configured = false;
@@ -687,7 +758,9 @@ static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_r
             DKMC_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
             configured = true;
         }
-        int grid = ctx->num_sms * 3;
+        // three CTAs (3 x 74 KB of stages) fill an SM; two while the pairwise kernel shares it
+        static const int cps_alone = [] { const char *e = getenv("DKMC_SPMV_CPS"); return e ? atoi(e) : 3; }();
+        int grid = ctx->num_sms * (ctx->pw_pending.active ? 2 : cps_alone);
         if (grid > ntiles) grid = ntiles;
         DKMC_LAUNCH(ctx, spmv_tma_kernel<MODE>, grid, kTmaThreads, kTmaSmemBytes, ntiles, nnz, d_row_ptr, d_col, d_val, d_x,
                     d_y, tile_info, w, dinv, partials, counter, dot_out, done_flag);
@@ -701,12 +774,13 @@ static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_r
 // Preconditioned CG on A x = b starting from x (in/out).  w.P must be set.
 static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                    const double *d_b, double *d_x, const CgWork &w, double tol, int max_iter, int check_every,
-                   int *iters_out, int *converged, double *bb_out) {
+                   int *iters_out, int *converged, double *bb_out, int x_readable) {
     const int vg = vec_grid(ctx, m);
+    const int own = m + 32;  // the arena's buffers carry at least 256 bytes of slack
     // r = b - A x, then z/p/rz/bb
     int rc0;
     if ((rc0 = launch_spmv<2>(ctx, w.num_tiles, m, nnz, d_row_ptr, d_col, d_val, d_x, w.r[0], w.tile_row, d_b, w.dinv,
-                              w.partials, &w.sc->cnt_c, &w.sc->resnorm2, nullptr))) return rc0;
+                              w.partials, &w.sc->cnt_c, &w.sc->resnorm2, nullptr, x_readable))) return rc0;
     DKMC_LAUNCH(ctx, cg_init_kernel, vg, kVecThreads, 0, m, w.r[0], d_b, w.P, w.p, tol, max_iter, w.partials, w.sc);
     CgScalars h;
     memset(&h, 0, sizeof(h));
@@ -716,7 +790,7 @@ static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const in
     while (true) {
         for (int k = 0; k < check_every; ++k) {
             if ((rc0 = launch_spmv<1>(ctx, w.num_tiles, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap, w.tile_row, w.p, nullptr,
-                                      w.partials, &w.sc->cnt_c, &w.sc->pAp, &w.sc->done))) return rc0;
+                                      w.partials, &w.sc->cnt_c, &w.sc->pAp, &w.sc->done, own))) return rc0;
             DKMC_LAUNCH(ctx, cg_update_kernel, vg, kVecThreads, 0, m, d_x, w.r[cur], w.r[cur ^ 1], w.p, w.Ap, w.P,
                         w.partials, w.sc, g_flags);
             cur ^= 1;
@@ -788,10 +862,10 @@ static int true_residual(dkmc_ctx *ctx, int m, const int *d_row_ptr, const int *
 
 static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
                          const double *d_val, const double *d_rhs, double *d_x, CgWork &w,
-                         const dkmc_solver_opts &o, dkmc_solve_info *info) {
+                         const dkmc_solver_opts &o, dkmc_solve_info *info, int x_readable) {
     int iters = 0, conv = 0, total = 0, rc;
     double bb0 = 0.0, rel = 0.0, est = 0.0;
-    if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o.rel_tol, o.max_iter, o.check_every, &iters, &conv, &bb0))) return rc;
+    if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o.rel_tol, o.max_iter, o.check_every, &iters, &conv, &bb0, x_readable))) return rc;
     total += iters;
     bool all_conv = conv != 0;
     const int vg = vec_grid(ctx, m);
@@ -803,7 +877,7 @@ static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, co
     if ((rc = true_residual(ctx, m, d_row_ptr, d_col, d_val, d_rhs, d_x, w, bb0, &rel, &est))) return rc;
     while (rounds < o.refine_rounds && est > o.est_tol) {
         DKMC_LAUNCH(ctx, fill_kernel, vg, kVecThreads, 0, m, 0.0, w.e);
-        if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, w.res, w.e, w, o.refine_tol, o.max_iter, o.check_every, &iters, &conv, nullptr))) return rc;
+        if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, w.res, w.e, w, o.refine_tol, o.max_iter, o.check_every, &iters, &conv, nullptr, m + 32))) return rc;
         total += iters;
         DKMC_LAUNCH(ctx, axpy_kernel, vg, kVecThreads, 0, m, 1.0, w.e, d_x);
         ++rounds;
@@ -998,7 +1072,7 @@ static int dist_grid(const dkmc_ctx *ctx, int n) {
 
 static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                     const double *d_b, double *d_x, const DistWork &d, double tol, int max_iter, int check_every,
-                    int *iters_out, int *converged) {
+                    int *iters_out, int *converged, int x_readable) {
     DistState *ds = dist_of(ctx);
     const CgWork &w = d.w;
     const int nt = d.t1 - d.t0, rows = d.rb - d.ra, vg = dist_grid(ctx, rows), n = d.n_cl;
@@ -1006,7 +1080,7 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
     int rc;
     if ((rc = halo_exchange(ctx, d, d_x))) return rc;
     if ((rc = launch_spmv<2>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, d_x, r, w.tile_row + d.t0, d_b, w.dinv, w.partials,
-                             &w.sc->cnt_c, &w.sc->resnorm2, nullptr))) return rc;
+                             &w.sc->cnt_c, &w.sc->resnorm2, nullptr, x_readable))) return rc;
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.dinv, w.partials, &w.sc->cnt_a, d.red + 1);
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, d_b, w.dinv, w.partials, &w.sc->cnt_a, d.red + 2);
     if (n > 0) {
@@ -1025,7 +1099,7 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
             if ((rc = halo_exchange(ctx, d, w.p))) return rc;
             if (nt > 0) {
                 if ((rc = launch_spmv<1>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap, w.tile_row + d.t0, w.p, nullptr,
-                                         w.partials, &w.sc->cnt_c, d.red + 0, &w.sc->done))) return rc;
+                                         w.partials, &w.sc->cnt_c, d.red + 0, &w.sc->done, m + 32))) return rc;
             } else
                 DKMC_CUDA(cudaMemsetAsync(d.red, 0, sizeof(double), ctx->stream));
             DKMC_NCCL(ncclAllReduce(d.red, d.red, 1, ncclDouble, ncclSum, ds->comm, ctx->stream));
@@ -1080,17 +1154,17 @@ __global__ void axpy_range_kernel(int ra, int rb, double a, const double *__rest
 
 static int dist_solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                               const double *d_rhs, double *d_x, DistWork &d, const dkmc_solver_opts &o,
-                              dkmc_solve_info *info) {
+                              dkmc_solve_info *info, int x_readable) {
     int iters = 0, conv = 0, total = 0, rc, rounds = 0;
     double est = 0.0;
     const int rows = d.rb - d.ra, vg = dist_grid(ctx, rows);
-    if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, d, o.rel_tol, o.max_iter, o.check_every, &iters, &conv))) return rc;
+    if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, d, o.rel_tol, o.max_iter, o.check_every, &iters, &conv, x_readable))) return rc;
     total += iters;
     bool all_conv = conv != 0;
     if ((rc = dist_true_residual(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, d, &est))) return rc;
     while (rounds < o.refine_rounds && est > o.est_tol) {
         DKMC_CUDA(cudaMemsetAsync(d.w.e, 0, (size_t)m * sizeof(double), ctx->stream));
-        if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d.w.res, d.w.e, d, o.refine_tol, o.max_iter, o.check_every, &iters, &conv))) return rc;
+        if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d.w.res, d.w.e, d, o.refine_tol, o.max_iter, o.check_every, &iters, &conv, m + 32))) return rc;
         total += iters;
         if (rows > 0) DKMC_LAUNCH(ctx, axpy_range_kernel, vg, kVecThreads, 0, d.ra, d.rb, 1.0, d.w.e, d_x);
         ++rounds;
@@ -1117,6 +1191,21 @@ int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_
                           nullptr, nullptr, nullptr);
 }
 
+int dkmc_spmv_window(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
+                     const double *d_x, int x_readable, double *d_y) {
+    DKMC_REQUIRE(ctx && d_row_ptr && d_col && d_val && d_x && d_y, "null pointer");
+    const WinFormat &wf = ctx->win;
+    DKMC_REQUIRE(wf.ok && wf.row_ptr == d_row_ptr && wf.val_tag == d_val,
+                 "the window-staged format holds another matrix (or this pattern exceeds its limits): call dkmc_assemble_K first");
+    DKMC_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 63) == 0 && x_readable >= ((m + 7) & ~7),
+                 "x must be 64-byte aligned and readable up to the next multiple of 8 entries");
+    const int4 *tile_row;
+    int num_tiles, rc;
+    if ((rc = get_tiling(ctx, m, nnz, d_row_ptr, &tile_row, &num_tiles))) return rc;
+    return launch_spmv<0>(ctx, num_tiles, m, nnz, d_row_ptr, d_col, d_val, d_x, d_y, tile_row, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, x_readable);
+}
+
 int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd, double high_G,
                     double low_G, const int *d_site_element, const int *d_site_charge, const int *d_metals,
                     int num_metals, double *d_val, double *d_rhs) {
@@ -1127,11 +1216,21 @@ int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int N
     int rc;
     if ((rc = ensure<unsigned char>(ctx, S_CLASS, N, &cls))) return rc;
     if ((rc = ensure<double>(ctx, S_CG_DINV, sp->m, &dinv))) return rc;
+    // the window-staged SpMV format of this pattern (built on first use): the assembly refreshes its
+    // per-step part (high_G bits, diagonal) alongside the CSR values
+    const int4 *tile_row;
+    int num_tiles;
+    if ((rc = get_tiling(ctx, sp->m, sp->nnz, sp->d_row_ptr, &tile_row, &num_tiles))) return rc;
+    if ((rc = get_win_format(ctx, sp->m, sp->nnz, sp->d_row_ptr, sp->d_col, tile_row, num_tiles))) return rc;
+    WinFormat &wf = ctx->win;
+    const bool win_ok = wf.ok;
+    if (wf.val_tag == d_val) wf.val_tag = nullptr;
     DKMC_LAUNCH(ctx, site_class_kernel, ceil_div(N, 256), 256, 0, N, d_site_element, d_site_charge, d_metals,
                 num_metals, cls);
     DKMC_LAUNCH(ctx, assemble_kernel, ceil_div(sp->m, 128), 128, 0, sp->m, N, NL, NR, Vd, high_G, low_G, cls,
                 sp->d_row_ptr, sp->d_col, sp->d_left_row_ptr, sp->d_left_col, sp->d_right_row_ptr, sp->d_right_col,
-                d_val, d_rhs, dinv);
+                d_val, d_rhs, dinv, win_ok ? wf.code_base : nullptr, win_ok ? wf.code : nullptr, win_ok ? wf.diag : nullptr);
+    if (win_ok) { wf.val_tag = d_val; wf.m_high = -high_G; wf.m_low = -low_G; }
     return DKMC_OK;
 }
 
@@ -1146,7 +1245,7 @@ int dkmc_solve_cg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int
     if ((rc = cg_workspace(ctx, m, nnz, d_row_ptr, &w))) return rc;
     DKMC_LAUNCH(ctx, diag_inverse_kernel, ceil_div(m, 256), 256, 0, m, d_row_ptr, d_col, d_val, w.dinv);
     DKMC_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
-    rc = solve_refined(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o, info);
+    rc = solve_refined(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o, info, m);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
     DKMC_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
     DKMC_CUDA(cudaEventSynchronize(ctx->ev_b));
@@ -1206,7 +1305,7 @@ int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int
     }
     // warm start: the interior of the previous potential (potential_solver_gpu.cu:754)
     double *x = d_site_potential_boundary + NL;
-    rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info);
+    rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info, m + NR);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
     // Dirichlet contacts (potential_solver.cpp:389-403 / potential_solver_gpu.cu:768-771)
     if (NL > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NL, 256), 256, 0, NL, -Vd / 2, d_site_potential_boundary);
@@ -1311,7 +1410,7 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
     }
     if ((rc = ensure<double>(ctx, S_DIST_RED, (size_t)4 + 2 * (size_t)d.n_cl + 8, &d.red))) return rc;
     double *x = d_site_potential_boundary + NL;
-    rc = dist_solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, d, o, info);
+    rc = dist_solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, d, o, info, m + NR);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
     // all-gather of the solution: every rank broadcasts its rows
     DKMC_NCCL(ncclGroupStart());

@@ -306,30 +306,40 @@ class Device:
         return {}
 
     def updatePotential(self, gpubuf: "GPUBuffers", p: KMCParameters, Vd: float, kmc_step_count: int = 0,
-                        opts: Optional[SolverOpts] = None, n_contact: Optional[int] = None) -> dict:
+                        opts: Optional[SolverOpts] = None, n_contact: Optional[int] = None,
+                        overlap: bool = True) -> dict:
         """potential_solver.cpp:232-285.  n_contact: contact size; the reference's GPU branch uses
         num_atoms_first_layer (:240-241), its CPU branch num_atoms_contact (:271)."""
         lib = self.ctx.lib
         nc = p.num_atoms_first_layer if n_contact is None else n_contact
         sp = gpubuf.sparsity(nc, nc)
         info = SolveInfo()
+        pw_args = (self.ctx.h, self.pbc, gpubuf.N_, _ptr(gpubuf.lattice), _ptr(gpubuf.sigma), _ptr(gpubuf.k),
+                   _ptr(gpubuf.site_x), _ptr(gpubuf.site_y), _ptr(gpubuf.site_z), _ptr(gpubuf.site_charge))
+        if overlap:
+            # the pairwise sum (FP64 pipe) goes to the side stream and shares the SMs with the CG (HBM)
+            check(lib.dkmc_poisson_gridless_begin(*pw_args, 0, gpubuf.N_, _ptr(gpubuf.site_potential_charge)))
         st = lib.dkmc_background_potential_sparse(
             self.ctx.h, C.byref(sp), self.N, gpubuf.nn_, _ptr(gpubuf.neigh_idx), nc, nc, float(Vd),
             float(p.high_G), float(p.low_G), _ptr(gpubuf.site_element), _ptr(gpubuf.site_charge),
             _ptr(gpubuf.metal_types), gpubuf.num_metal_types_, _ptr(gpubuf.site_potential_boundary),
             C.byref(opts) if opts is not None else None, C.byref(info))
+        pw_ms = C.c_double(0.0)
+        if overlap:
+            check(lib.dkmc_poisson_gridless_join(self.ctx.h, C.byref(pw_ms)))
         check(st, allow=(_capi.DKMC_ERR_NOT_CONVERGED,))
-        torch = _torch()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        check(lib.dkmc_poisson_gridless(self.ctx.h, self.pbc, gpubuf.N_, _ptr(gpubuf.lattice), _ptr(gpubuf.sigma),
-                                        _ptr(gpubuf.k), _ptr(gpubuf.site_x), _ptr(gpubuf.site_y), _ptr(gpubuf.site_z),
-                                        _ptr(gpubuf.site_charge), _ptr(gpubuf.site_potential_charge)))
-        e1.record()
-        e1.synchronize()
-        return {"pairwise_ms": e0.elapsed_time(e1), "cg_iterations": info.iterations, "cg_rel_residual": info.rel_residual,
+        if not overlap:
+            torch = _torch()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib.dkmc_poisson_gridless(*pw_args, _ptr(gpubuf.site_potential_charge)))
+            e1.record()
+            e1.synchronize()
+            pw_ms.value = e0.elapsed_time(e1)
+        return {"pairwise_ms": pw_ms.value, "cg_iterations": info.iterations, "cg_rel_residual": info.rel_residual,
                 "cg_est_error": info.est_error, "cg_refinements": info.refinements,
-                "cg_converged": st == _capi.DKMC_OK, "assemble_ms": info.assemble_ms, "solve_ms": info.solve_ms}
+                "cg_converged": st == _capi.DKMC_OK, "assemble_ms": info.assemble_ms, "solve_ms": info.solve_ms,
+                "overlap": bool(overlap)}
 
 
 class GPUBuffers:

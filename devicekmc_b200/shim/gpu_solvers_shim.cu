@@ -101,9 +101,16 @@ void background_potential_gpu_sparse(cublasHandle_t, cusolverDnHandle_t, GPUBuff
                                      const int N_left_tot, const int N_right_tot, const double d_Vd, const int pbc,
                                      const double d_high_G, const double d_low_G, const double nn_dist,
                                      const int num_metals, int kmc_step_count) {
-    (void)pbc; (void)nn_dist; (void)kmc_step_count;
+    (void)nn_dist; (void)kmc_step_count;
     dkmc_sparsity sp = sparsity_of(gpubuf, N - N_left_tot - N_right_tot);
     dkmc_solve_info info = {};
+    // Device::updatePotential (potential_solver.cpp:249-260) calls poisson_gridless_gpu on the same
+    // gpubuf right after this function: start that sum now on the side stream so that it overlaps
+    // the CG; the poisson_gridless_gpu call below then only joins it.
+    report(dkmc_poisson_gridless_begin(ctx(), pbc, gpubuf.N_, gpubuf.lattice, gpubuf.sigma, gpubuf.k, gpubuf.site_x,
+                                       gpubuf.site_y, gpubuf.site_z, gpubuf.site_charge, 0, gpubuf.N_,
+                                       gpubuf.site_potential_charge),
+           "poisson_gridless_gpu (early start)");
     int st = dkmc_background_potential_sparse(ctx(), &sp, N, gpubuf.nn_, gpubuf.neigh_idx, N_left_tot, N_right_tot, d_Vd,
                                               d_high_G, d_low_G, reinterpret_cast<const int *>(gpubuf.site_element),
                                               gpubuf.site_charge, reinterpret_cast<const int *>(gpubuf.metal_types),
@@ -117,6 +124,7 @@ void poisson_gridless_gpu(const int num_atoms_contact, const int pbc, const int 
                           const double *sigma, const double *k, const double *posx, const double *posy,
                           const double *posz, const int *site_charge, double *site_potential_charge) {
     (void)num_atoms_contact;
+    // joins the sum started in background_potential_gpu_sparse when the arguments match, else computes
     report(dkmc_poisson_gridless(ctx(), pbc, N, lattice, sigma, k, posx, posy, posz, site_charge, site_potential_charge),
            "poisson_gridless_gpu");
 }

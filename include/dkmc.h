@@ -130,6 +130,13 @@ int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int N
 /* y = A x, CSR FP64/int32 (replaces cusparseSpMV, iterative_solvers_gpu.cu:411,428) */
 int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
               const double *d_val, const double *d_x, double *d_y);
+/* The same product by the kernel the CG of dkmc_background_potential_sparse uses: K has two distinct
+ * off-diagonal values and a static pattern, so dkmc_assemble_K also keeps a window-staged form of
+ * the matrix it assembled last (2 bytes per non-zero, x pieces bulk-copied to shared memory).  d_val
+ * must be that matrix; d_x 64-byte aligned with x_readable >= m rounded up to 8 readable entries.
+ * Bit-identical to dkmc_spmv.  DKMC_ERR_ARG if the pattern exceeds the format's limits. */
+int dkmc_spmv_window(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
+                     const double *d_val, const double *d_x, int x_readable, double *d_y);
 int dkmc_solve_cg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
                   const double *d_val, const double *d_rhs, double *d_x,
                   const dkmc_solver_opts *opts, dkmc_solve_info *info);
@@ -146,6 +153,23 @@ int dkmc_poisson_gridless_rows(dkmc_ctx *ctx, int pbc, int N, const double *d_la
                                const double *d_sigma, const double *d_k, const double *d_x,
                                const double *d_y, const double *d_z, const int *d_site_charge,
                                int row_begin, int row_end, double *d_site_potential_charge);
+
+/* Device::updatePotential (potential_solver.cpp:249-260) calls the CG and then the pairwise sum; they
+ * are independent (both read only site_charge) and bound by different units (HBM vs the FP64 pipe).
+ * _begin compacts the charged sites on the context's stream, then launches the sum on the context's
+ * SIDE stream with a bounded residency per SM and returns at once; work issued afterwards on the
+ * context's stream (dkmc_background_potential_sparse) runs concurrently with it.  _join makes the
+ * context's stream wait for the sum, blocks until it is complete and reports its device time.
+ * A dkmc_poisson_gridless(_rows) call with the same arguments as a pending _begin joins it instead
+ * of recomputing — that is how the reference-named shim overlaps the two without touching
+ * Device::updatePotential.  The inputs must not change between _begin and _join. */
+int dkmc_poisson_gridless_begin(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice,
+                                const double *d_sigma, const double *d_k, const double *d_x,
+                                const double *d_y, const double *d_z, const int *d_site_charge,
+                                int row_begin, int row_end, double *d_site_potential_charge);
+int dkmc_poisson_gridless_join(dkmc_ctx *ctx, double *pairwise_ms);
+/* CTAs per SM the overlapped pairwise kernel may occupy (default 6 of the 10 that fit) */
+int dkmc_ctx_set_pairwise_share(dkmc_ctx *ctx, int blocks_per_sm);
 
 /* ---- a7: rate table.  build_event_list, kmc_events.cu:34-126 with the CPU semantics of
  * KMCProcess::update_events_and_rates, KMCProcess.cpp:67-164 (vacancy-diffusion barrier from
