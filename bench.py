@@ -105,11 +105,14 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------- CPU arm
-def cpu_step_sample(name, threads=None, pair_rows=None, Vd=10.0):
+def cpu_step_sample(name, threads=None, pair_rows=None, Vd=10.0, events_per_step=850, event_sample=300):
     """One KMC step of the oracle (CPU restatement of the reference's algorithm, sparse K) on
-    the same workload.  The pairwise O(N*N_charged) sum is timed on a bounded sample of target
-    rows and scaled to N.  The reference's own CPU build (oracle/_ref) cannot run this workload:
-    it allocates a dense N x N K (potential_solver.cpp:301) = 8.5 TB at 1 M sites."""
+    the same workload, as a BOUNDED sample (~20-30 s): the pairwise O(N*N_charged) sum is timed on
+    a sample of target rows and scaled to N; the residence-time loop is timed on its first
+    `event_sample` events and scaled to `events_per_step` (what the GPU arm executes per step on
+    this workload); every other stage runs in full.  The reference's own CPU build (oracle/_ref)
+    cannot run this workload: it allocates a dense N x N K (potential_solver.cpp:301) = 8.5 TB at
+    1 M sites."""
     from oracle import oracle as O
     threads = threads or os.cpu_count()
     os.environ["OMP_NUM_THREADS"] = str(threads)
@@ -138,10 +141,15 @@ def cpu_step_sample(name, threads=None, pair_rows=None, Vd=10.0):
     et, ep = O.rate_table(nb, layer, lat, p.pbc, p.background_temp, p.freq, p.sigma, p.k, x, y, z, pb, pc, el, q, E)
     t["rate_table"] = time.perf_counter() - t0
     rng = O.Rng(1)
-    t0 = time.perf_counter(); tt, ev, el2, q2 = O.kmc_events(nb, et, ep, el, q, p.freq, rng); t["event_loop"] = time.perf_counter() - t0
-    step_s = t["charge"] + t["potential_boundary"] + t["pairwise_scaled"] + t["rate_table"] + t["event_loop"]
-    sample = (f"oracle port, 1 step of {name} (N={N}, N_charged={ncharged}, {int(info[0])} CG its, {len(ev)} events); "
-              f"pairwise timed on {rows} of {N} target rows and scaled; all other stages in full")
+    O.set_event_limit(event_sample)
+    t0 = time.perf_counter(); tt, ev, el2, q2 = O.kmc_events(nb, et, ep, el, q, p.freq, rng); t["event_loop_sample"] = time.perf_counter() - t0
+    O.set_event_limit(0)
+    n_ev = max(len(ev), 1)
+    t["event_loop_scaled"] = t["event_loop_sample"] * events_per_step / n_ev
+    step_s = t["charge"] + t["potential_boundary"] + t["pairwise_scaled"] + t["rate_table"] + t["event_loop_scaled"]
+    sample = (f"oracle port, 1 step of {name} (N={N}, N_charged={ncharged}, {int(info[0])} CG its); pairwise timed on "
+              f"{rows} of {N} target rows and scaled; event loop timed on its first {n_ev} events and scaled to "
+              f"{events_per_step} events per step; all other stages in full")
     return 1.0 / step_s, threads, sample, t
 
 
@@ -150,8 +158,8 @@ def reference_arm(args):
     if rank != 0:
         return
     vals, smp, tim = [], "", {}
-    for s in range(max(1, min(args.steps, 2))):
-        v, cores, smp, tim = cpu_step_sample(args.workload)
+    for s in range(max(1, min(args.steps, 3))):
+        v, cores, smp, tim = cpu_step_sample(args.workload, events_per_step=args.events_per_step)
         vals.append(v)
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -196,10 +204,14 @@ def gpu_arm(args):
         if e2e:
             buf.sync_HostToGPU(dev)
         dev.updateCharge(buf, p.metals)
+        ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ep0.record()
         o = dev.updatePotential(buf, p, Vd, n_contact=nc)
+        ep1.record()
         sim.executeKMCStep(buf, dev)
         if e2e:
             buf.sync_GPUToHost(dev)
+        o["potential_ms"] = ep0.elapsed_time(ep1)
         i = sim.last_info
         o.update(events=i.n_events, fallbacks=i.n_exact_fallbacks, rate_ms=i.rate_ms, loop_ms=i.loop_ms)
         return o
@@ -249,7 +261,18 @@ def gpu_arm(args):
     fp64 = C.c_double(0)
     check(lib.dkmc_probe_fp64_tflops(dev.ctx.h, C.byref(fp64)))
     ncharged = int((buf.site_charge != 0).sum().item())
-    pair_ms = float(np.median([s["pairwise_ms"] for s in stats]))
+    # the pairwise kernel alone (inside a step it shares the SMs with the CG)
+    for _ in range(2):
+        check(lib.dkmc_poisson_gridless(dev.ctx.h, dev.pbc, dev.N, buf.lattice.data_ptr(), buf.sigma.data_ptr(), buf.k.data_ptr(),
+                                        buf.site_x.data_ptr(), buf.site_y.data_ptr(), buf.site_z.data_ptr(),
+                                        buf.site_charge.data_ptr(), buf.site_potential_charge.data_ptr()))
+    e0.record()
+    for _ in range(3):
+        check(lib.dkmc_poisson_gridless(dev.ctx.h, dev.pbc, dev.N, buf.lattice.data_ptr(), buf.sigma.data_ptr(), buf.k.data_ptr(),
+                                        buf.site_x.data_ptr(), buf.site_y.data_ptr(), buf.site_z.data_ptr(),
+                                        buf.site_charge.data_ptr(), buf.site_potential_charge.data_ptr()))
+    e1.record(); e1.synchronize()
+    pair_ms = e0.elapsed_time(e1) / 3
     pairs = float(dev.N) * ncharged - ncharged
     pair_tflops = 200.0 * pairs / (pair_ms * 1e-3) / 1e12
     # scan primitive over the N*nn rate table
@@ -264,8 +287,13 @@ def gpu_arm(args):
     scan_ms = e0.elapsed_time(e1) / 10
     rate_ms = float(np.median([s["rate_ms"] for s in stats]))
     med = lambda k: float(np.median([s[k] for s in stats]))
-    shares = {"assemble": med("assemble_ms"), "cg_solve": med("solve_ms"), "pairwise": pair_ms, "rate_table": rate_ms,
-              "event_loop": med("loop_ms")}
+    # cg_solve and pairwise run CONCURRENTLY (main / side stream): "potential" is the wall time of both
+    shares = {"potential": med("potential_ms"), "assemble": med("assemble_ms"), "cg_solve": med("solve_ms"),
+              "pairwise": med("pairwise_ms"), "rate_table": rate_ms, "event_loop": med("loop_ms")}
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {})
     rooflines = {
         "spmv": {"bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
                  "traffic": None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "peak_source": peak_src},
@@ -278,14 +306,16 @@ def gpu_arm(args):
         "scan": {"bound": "hbm", "achieved": 16.0 * n_tab / (scan_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                  "frac": 16.0 * n_tab / (scan_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
     }
-    dominant = max(shares, key=shares.get)
+    for k_, r_ in rooflines.items():
+        r_["traffic"] = traffic.get(k_)
+    dominant = max((k_ for k_ in shares if k_ != "potential"), key=shares.get)
     roof_key = {"pairwise": "pairwise", "cg_solve": "spmv", "assemble": "spmv", "rate_table": "rate_table",
                 "event_loop": "rate_table"}[dominant]
     roofline = dict(rooflines[roof_key]); roofline["kernel"] = roof_key; roofline["dominant_stage"] = dominant
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, cores, smp, tim = cpu_step_sample(args.workload)
+        v, cores, smp, tim = cpu_step_sample(args.workload, events_per_step=int(np.median([s["events"] for s in stats])))
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": smp,
                "stage_seconds": {k: round(t, 4) for k, t in tim.items()}}
 
@@ -293,7 +323,8 @@ def gpu_arm(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "sites": dev.N, "nn": buf.nn_, "interior_rows": m, "nnz": nnz,
-                       "n_charged": ncharged, "Vd": Vd, "l2": "inputs larger than L2 (matrix 12*nnz bytes, rate table 16*N*nn bytes)",
+                       "n_charged": ncharged, "Vd": Vd, "overlap": "pairwise sum on a side stream, concurrent with the CG",
+                       "l2": "inputs larger than L2 (matrix 12*nnz bytes, rate table 16*N*nn bytes)",
                        "init_seconds": round(init_s, 3)},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": buf.h2d_bytes(), "d2h_bytes_per_step": buf.d2h_bytes()},
@@ -313,6 +344,9 @@ def main():
     ap.add_argument("--workload", default="tiled_1M")
     ap.add_argument("--vd", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--events-per-step", type=int, default=850,
+                    help="--impl reference: events per KMC step the bounded event-loop sample is scaled to "
+                         "(what the GPU arm executes per step on tiled_1M after warm-up)")
     ap.add_argument("--replicated-cg", action="store_true", help="N>1: keep the CG on every rank (only the pairwise sum is sharded)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -20,6 +20,7 @@ constexpr int kNumSlots = 48;
 constexpr int kMaxLevels = 8;
 
 void set_error(const char *fmt, ...);
+int window_carveout();  // shared-memory carve-out (percent) common to the kernels of the overlap window
 
 #define DKMC_CUDA(call)                                                                       \
     do {                                                                                      \
@@ -68,12 +69,13 @@ struct WinFormat {
     int m = 0, nnz = 0, num_tiles = 0;
     bool ok = false;                     // every tile fits the format's limits
     int fail_bits = 0, max_chunk = 0;
-    unsigned short *code_base = nullptr; // static: window position | diagonal bit
-    unsigned short *code = nullptr;      // per step: code_base | high_G bit
-    int *rp = nullptr;                   // padded row_ptr
-    double *diag = nullptr;              // per step: diagonal of K
-    void *hdr = nullptr, *runs = nullptr;
-    const double *val_tag = nullptr;     // the assembled CSR values `code`/`diag` correspond to
+    size_t blob_bytes = 0;
+    unsigned char *blobs = nullptr;      // per tile: header, runs, codes, row starts, row order, diagonal
+    void *plan = nullptr;                // int4 per tile: (blob offset / 128, blob bytes, window doubles, -)
+    unsigned short *code_base = nullptr; // static, CSR-indexed: window position | diagonal bit
+    int *code_pos = nullptr;             // per row: halfword index into `blobs` of the row's first code
+    int *diag_pos = nullptr;             // per row: double index into `blobs` of the row's diagonal entry
+    const double *val_tag = nullptr;     // the assembled CSR values the blobs correspond to
     double m_high = 0.0, m_low = 0.0;    // -high_G, -low_G
 };
 
@@ -97,6 +99,7 @@ struct dkmc_ctx {
     } grid;
     dkmc::SpmvTiling tiling;
     dkmc::WinFormat win;
+    int use_window_spmv = 0;   // opt-in (dkmc_ctx_set_window_spmv / DKMC_WINDOW_SPMV=1)
     // event loop state for dkmc_kmc_step_continue
     struct {
         int N = 0, nn = 0;
@@ -121,7 +124,8 @@ struct dkmc_ctx {
         const int *d_charge = nullptr;
         double *d_out = nullptr;
     } pw_pending;
-    int pw_side_blocks_per_sm = 6;   // residency of the pairwise kernel while it shares the SMs with the CG
+    int pw_side_threads = 128;
+    int pw_side_blocks_per_sm = 3;   // residency of the pairwise kernel while it shares the SMs with the CG
 };
 
 namespace dkmc {
@@ -146,15 +150,16 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Files whose kernels run while the pairwise sum shares the SMs with the CG define
 // DKMC_CARVEOUT_MAXSHARED: the L1/shared split of an SM cannot change while CTAs are resident, so
-// every kernel of that window asks for the same (largest shared memory) carve-out — otherwise a
-// CTA that needs another split waits until the SM has drained.
+// every kernel of that window asks for the SAME carve-out (window_carveout(): 60 % shared memory,
+// the rest L1 for the SpMV's x gathers) — otherwise a CTA that needs another split waits until the
+// SM has drained, which serialises the two streams.
 #ifdef DKMC_CARVEOUT_MAXSHARED
 #define DKMC_SET_CARVEOUT(kernel)                                                             \
     do {                                                                                      \
         static bool cfg__ = false;                                                            \
         if (!cfg__) {                                                                         \
             cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,      \
-                                 (int)cudaSharedmemCarveoutMaxShared);                        \
+                                 ::dkmc::window_carveout());                                  \
             cfg__ = true;                                                                     \
         }                                                                                     \
     } while (0)

@@ -16,9 +16,14 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int window_carveout() {
+    static const int pct = [] { const char *e = getenv("DKMC_CARVEOUT"); int v = e ? atoi(e) : 60; return v < 0 ? 0 : (v > 100 ? 100 : v); }();
+    return pct;
+}
+
 void free_win_format(dkmc_ctx *ctx) {
     WinFormat &w = ctx->win;
-    void *ptrs[6] = {w.code_base, w.code, w.rp, w.diag, w.hdr, w.runs};
+    void *ptrs[5] = {w.blobs, w.plan, w.code_base, w.code_pos, w.diag_pos};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     w = WinFormat();
@@ -96,6 +101,7 @@ int dkmc_ctx_create(dkmc_ctx **out) {
     DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     DKMC_CUDA(cudaEventCreate(&ctx->ev_pw0));
     DKMC_CUDA(cudaEventCreate(&ctx->ev_pw1));
+    if (const char *e = getenv("DKMC_WINDOW_SPMV")) ctx->use_window_spmv = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DKMC_PW_SIDE_BPS")) { int v = atoi(e); if (v > 0) ctx->pw_side_blocks_per_sm = v; }
     *out = ctx;
     return DKMC_OK;

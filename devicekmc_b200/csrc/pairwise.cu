@@ -14,10 +14,11 @@
 
 namespace dkmc {
 
-constexpr int kPwThreads = 128;
+constexpr int kPwThreads = 128;      // CTA size when the sum has the GPU to itself
+constexpr int kPwMaxThreads = 256;   // the CTA size is a launch parameter (targets per tile = 2 x CTA size)
 constexpr int kPwTile = 256;       // charged sources per shared-memory tile
 constexpr int kCompactBlock = 1024;
-constexpr int kPwFullBlocksPerSm = 10;  // 48 registers x 128 threads: ten CTAs fill an SM
+constexpr int kPwFullBlocksPerSm = 6;   // ~80 registers x 128 threads: six CTAs fill an SM
 
 struct __align__(32) ChargedSite { double x, y, z, q; };
 
@@ -108,28 +109,44 @@ __device__ __forceinline__ double erfc_fast(double t) {
     return t < 26.45 ? g * e : 0.0;  // erfc < 1e-305 beyond: contributes nothing at 1e-10
 }
 
-// phi_c[i] = k q_e sum_j q_j erfc(r_ij / (sigma sqrt 2)) / r_ij.  One target per thread, sources
-// staged in shared memory, two independent sources per iteration for ILP, no atomics.
-// Persistent CTAs: each fetches tiles of kPwThreads targets from an atomic counter, so the launch
+// phi_c[i] = k q_e sum_j q_j erfc(r_ij / (sigma sqrt 2)) / r_ij.  Two targets per thread, sources
+// staged in shared memory, two sources per iteration: four independent FP64 chains per thread keep
+// the FP64 pipe busy with few resident warps (the kernel shares the SMs with the CG), no atomics.
+// Persistent CTAs: each fetches tiles of 2 x blockDim targets from an atomic counter, so the launch
 // can be sized to a chosen residency per SM (the whole SM when the sum runs alone, a share of it
 // when it runs beside the CG on the side stream).  Every target's sum runs over the compacted
-// sources in ascending site order, so the result does not depend on the tile schedule.
+// sources in ascending site order (even and odd sources in two accumulators), so the result does
+// not depend on the tile schedule.
 template <bool PBC>
-__global__ void __launch_bounds__(kPwThreads) pairwise_kernel(
+__global__ void __launch_bounds__(kPwMaxThreads) pairwise_kernel(
     int row_begin, int row_end, const double *__restrict__ x, const double *__restrict__ y,
     const double *__restrict__ z, const int *__restrict__ n_src_ptr, const ChargedSite *__restrict__ src,
     const int *__restrict__ src_idx, const double *__restrict__ lattice, const double *__restrict__ sigma_ptr,
-    const double *__restrict__ k_ptr, int *tile_counter, double *__restrict__ out) {
+    const double *__restrict__ k_ptr, int *tile_counter, int *sm_count, int sm_quota, double *__restrict__ out) {
     __shared__ ChargedSite tile[kPwTile];
     __shared__ int tile_idx[kPwTile];
     __shared__ int s_tile;
+    // Even spread when the kernel shares the SMs with the CG: the launch holds more CTAs than wanted,
+    // every CTA registers on its SM, and those beyond the SM's quota leave at once (the tiles are
+    // fetched dynamically, so nobody's work is lost).  Without this the block scheduler may pack the
+    // persistent CTAs onto some of the SMs and leave the others to the CG alone.
+    if (sm_count != nullptr) {
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_tile = atomicAdd(sm_count + (smid & 255u), 1);
+        }
+        __syncthreads();
+        if (s_tile >= sm_quota) return;
+    }
     const int nsrc = *n_src_ptr;
     const double sigma = *sigma_ptr, kc = *k_ptr;
     const double ly = lattice[1], lz = lattice[2];
     const double inv_ly = 1.0 / ly, inv_lz = 1.0 / lz;
     const double cscale = 1e-10 / (sigma * sqrt(2.0));  // t = r[Angstrom] * cscale
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    const int n_tiles = (row_end - row_begin + kPwThreads - 1) / kPwThreads;
+    const int nthr = (int)blockDim.x, targets = 2 * nthr;
+    const int n_tiles = (row_end - row_begin + targets - 1) / targets;
 
     while (true) {
         __syncthreads();
@@ -137,12 +154,13 @@ __global__ void __launch_bounds__(kPwThreads) pairwise_kernel(
         __syncthreads();
         const int tile_id = s_tile;
         if (tile_id >= n_tiles) break;
-        const int i = row_begin + tile_id * kPwThreads + threadIdx.x;
-        const bool valid = i < row_end;
-        const double xi = valid ? x[i] : 0.0, yi = valid ? y[i] : 0.0, zi = valid ? z[i] : 0.0;
-        double acc0 = 0.0, acc1 = 0.0;
+        const int ia = row_begin + tile_id * targets + threadIdx.x, ib = ia + nthr;
+        const bool va = ia < row_end, vb = ib < row_end;
+        const double xa = va ? x[ia] : 0.0, ya = va ? y[ia] : 0.0, za = va ? z[ia] : 0.0;
+        const double xb = vb ? x[ib] : 0.0, yb = vb ? y[ib] : 0.0, zb = vb ? z[ib] : 0.0;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
 
-        auto pair_term = [&](const ChargedSite &s, int sidx) -> double {
+        auto pair_term = [&](double xi, double yi, double zi, int i, const ChargedSite &s, int sidx) -> double {
             double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
             if (PBC) {
                 dy = fma(-rint(dy * inv_ly), ly, dy);
@@ -159,20 +177,30 @@ __global__ void __launch_bounds__(kPwThreads) pairwise_kernel(
         for (int t0 = 0; t0 < nsrc; t0 += kPwTile) {
             const int nt = min(kPwTile, nsrc - t0);
             __syncthreads();
-            for (int t = threadIdx.x; t < nt; t += kPwThreads) {
+            for (int t = threadIdx.x; t < nt; t += nthr) {
                 tile[t] = src[t0 + t];
                 tile_idx[t] = src_idx[t0 + t];
             }
             __syncthreads();
             int t = 0;
             for (; t + 1 < nt; t += 2) {
-                acc0 += pair_term(tile[t], tile_idx[t]);
-                acc1 += pair_term(tile[t + 1], tile_idx[t + 1]);
+                const ChargedSite s0 = tile[t], s1 = tile[t + 1];
+                const int j0 = tile_idx[t], j1 = tile_idx[t + 1];
+                a0 += pair_term(xa, ya, za, ia, s0, j0);
+                b0 += pair_term(xb, yb, zb, ib, s0, j0);
+                a1 += pair_term(xa, ya, za, ia, s1, j1);
+                b1 += pair_term(xb, yb, zb, ib, s1, j1);
             }
-            if (t < nt) acc0 += pair_term(tile[t], tile_idx[t]);
+            if (t < nt) {
+                const ChargedSite s0 = tile[t];
+                const int j0 = tile_idx[t];
+                a0 += pair_term(xa, ya, za, ia, s0, j0);
+                b0 += pair_term(xb, yb, zb, ib, s0, j0);
+            }
         }
         // rinv is in 1/Angstrom: 1e10 converts to 1/m
-        if (valid) out[i] = (acc0 + acc1) * (kc * kElementaryCharge * 1e10);
+        if (va) out[ia] = (a0 + a1) * (kc * kElementaryCharge * 1e10);
+        if (vb) out[ib] = (b0 + b1) * (kc * kElementaryCharge * 1e10);
     }
 }
 
@@ -189,9 +217,9 @@ static int pairwise_prepare(dkmc_ctx *ctx, int N, const double *d_x, const doubl
     if ((rc = ensure<int>(ctx, S_SCAN_BLOCK, (size_t)ceil_div(nb, kScanTile) + 1, &tmp))) return rc;
     if ((rc = ensure<ChargedSite>(ctx, S_PW_SRC, (size_t)N, &src))) return rc;
     if ((rc = ensure<int>(ctx, S_PW_FLAGS, (size_t)N, &src_idx))) return rc;
-    if ((rc = ensure<int>(ctx, S_PW_TILECTR, 4, &tile_counter))) return rc;
+    if ((rc = ensure<int>(ctx, S_PW_TILECTR, 4 + 256, &tile_counter))) return rc;
     int *incl = counts + nb, *total = counts + 2 * nb;
-    DKMC_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), ctx->stream));
+    DKMC_CUDA(cudaMemsetAsync(tile_counter, 0, (1 + 256) * sizeof(int), ctx->stream));  // tile counter | CTAs per SM
     DKMC_LAUNCH(ctx, charged_count_kernel, nb, kCompactBlock, 0, N, d_site_charge, counts);
     if ((rc = inclusive_scan<int>(ctx, counts, nb, incl, tmp))) return rc;
     DKMC_LAUNCH(ctx, charged_scatter_kernel, nb, kCompactBlock, 0, N, nb, d_site_charge, d_x, d_y, d_z, counts, incl,
@@ -200,19 +228,26 @@ static int pairwise_prepare(dkmc_ctx *ctx, int N, const double *d_x, const doubl
     return DKMC_OK;
 }
 
-static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm, int pbc, int row_begin, int row_end,
+static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm, int threads, bool shared_sms, int pbc, int row_begin, int row_end,
                            const double *d_lattice, const double *d_sigma, const double *d_k, const double *d_x,
                            const double *d_y, const double *d_z, const ChargedSite *src, const int *src_idx,
                            const int *total, int *tile_counter, double *d_out) {
-    const int tiles = ceil_div(row_end - row_begin, kPwThreads);
+    const int tiles = ceil_div(row_end - row_begin, 2 * threads);
     int grid = ctx->num_sms * blocks_per_sm;
-    if (grid > tiles) grid = tiles;
+    int *sm_count = nullptr;
+    if (shared_sms) {  // launch what fits on an idle GPU; each SM keeps `blocks_per_sm` of them
+        const int fit = (kPwFullBlocksPerSm * kPwThreads) / threads;
+        grid = ctx->num_sms * (fit > blocks_per_sm ? fit : blocks_per_sm);
+        sm_count = tile_counter + 1;
+    } else if (grid > tiles) {
+        grid = tiles;
+    }
     if (pbc) {
-        DKMC_LAUNCH_ON(ctx, stream, pairwise_kernel<true>, grid, kPwThreads, 0, row_begin, row_end, d_x, d_y, d_z, total,
-                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, d_out);
+        DKMC_LAUNCH_ON(ctx, stream, pairwise_kernel<true>, grid, threads, 0, row_begin, row_end, d_x, d_y, d_z, total,
+                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm, d_out);
     } else {
-        DKMC_LAUNCH_ON(ctx, stream, pairwise_kernel<false>, grid, kPwThreads, 0, row_begin, row_end, d_x, d_y, d_z, total,
-                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, d_out);
+        DKMC_LAUNCH_ON(ctx, stream, pairwise_kernel<false>, grid, threads, 0, row_begin, row_end, d_x, d_y, d_z, total,
+                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm, d_out);
     }
     return DKMC_OK;
 }
@@ -240,7 +275,7 @@ int dkmc_poisson_gridless_begin(dkmc_ctx *ctx, int pbc, int N, const double *d_l
     DKMC_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
     DKMC_CUDA(cudaEventRecord(ctx->ev_pw0, ctx->side_stream));
     if (row_end > row_begin)
-        if ((rc = pairwise_launch(ctx, ctx->side_stream, ctx->pw_side_blocks_per_sm, pbc, row_begin, row_end, d_lattice,
+        if ((rc = pairwise_launch(ctx, ctx->side_stream, ctx->pw_side_blocks_per_sm, ctx->pw_side_threads, true, pbc, row_begin, row_end, d_lattice,
                                   d_sigma, d_k, d_x, d_y, d_z, src, src_idx, total, tile_counter,
                                   d_site_potential_charge))) return rc;
     DKMC_CUDA(cudaEventRecord(ctx->ev_pw1, ctx->side_stream));
@@ -285,7 +320,7 @@ int dkmc_poisson_gridless_rows(dkmc_ctx *ctx, int pbc, int N, const double *d_la
     int *src_idx, *total, *tile_counter;
     int rc;
     if ((rc = pairwise_prepare(ctx, N, d_x, d_y, d_z, d_site_charge, &src, &src_idx, &total, &tile_counter))) return rc;
-    if ((rc = pairwise_launch(ctx, ctx->stream, kPwFullBlocksPerSm, pbc, row_begin, row_end, d_lattice, d_sigma, d_k, d_x,
+    if ((rc = pairwise_launch(ctx, ctx->stream, kPwFullBlocksPerSm, kPwThreads, false, pbc, row_begin, row_end, d_lattice, d_sigma, d_k, d_x,
                               d_y, d_z, src, src_idx, total, tile_counter, d_site_potential_charge))) return rc;
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
     return DKMC_OK;
@@ -298,9 +333,12 @@ int dkmc_poisson_gridless(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice
                                       d_site_potential_charge);
 }
 
-int dkmc_ctx_set_pairwise_share(dkmc_ctx *ctx, int blocks_per_sm) {
+int dkmc_ctx_set_pairwise_share(dkmc_ctx *ctx, int blocks_per_sm, int threads_per_block) {
     DKMC_REQUIRE(ctx != nullptr && blocks_per_sm >= 1 && blocks_per_sm <= 16, "blocks_per_sm in 1..16");
+    DKMC_REQUIRE(threads_per_block >= 32 && threads_per_block <= kPwMaxThreads && threads_per_block % 32 == 0,
+                 "threads_per_block: a multiple of 32 up to 256");
     ctx->pw_side_blocks_per_sm = blocks_per_sm;
+    ctx->pw_side_threads = threads_per_block;
     return DKMC_OK;
 }
 

@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include <cstdlib>
+#include <vector>
 
 #define DKMC_CARVEOUT_MAXSHARED 1
 #include "common.cuh"
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(128) assemble_kernel(
     const unsigned char *__restrict__ cls, const int *__restrict__ row_ptr, const int *__restrict__ col,
     const int *__restrict__ lrp, const int *__restrict__ lcol, const int *__restrict__ rrp,
     const int *__restrict__ rcol, double *__restrict__ val, double *__restrict__ rhs,
-    double *__restrict__ dinv, const unsigned short *__restrict__ code_base, unsigned short *__restrict__ code,
-    double *__restrict__ diag_out) {
+    double *__restrict__ dinv, const unsigned short *__restrict__ code_base, const int *__restrict__ code_pos,
+    const int *__restrict__ diag_pos, unsigned char *__restrict__ blobs) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     const double VL = -Vd / 2, VR = Vd / 2;
@@ -76,10 +77,13 @@ __global__ void __launch_bounds__(128) assemble_kernel(
         diag = __dadd_rn(diag, G);
         ksub = __dadd_rn(ksub, __dmul_rn(-G, VL));
     }
-    int diag_pos = -1;
-    for (int p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
+    int dpos = -1;
+    // window-staged format (spmv_win.cuh): this row's codes and diagonal slot inside its tile's blob
+    const int row_begin = row_ptr[r];
+    unsigned short *code = blobs ? reinterpret_cast<unsigned short *>(blobs) + code_pos[r] - row_begin : nullptr;
+    for (int p = row_begin; p < row_ptr[r + 1]; ++p) {
         int c = col[p];
-        if (c == r) { diag_pos = p; continue; }
+        if (c == r) { dpos = p; continue; }
         const unsigned char cj = cls[c + NL];
         double G = conductance(ci, cj, high_G, low_G);
         val[p] = -G;
@@ -91,11 +95,11 @@ __global__ void __launch_bounds__(128) assemble_kernel(
         diag = __dadd_rn(diag, G);
         ksub = __dadd_rn(ksub, __dmul_rn(-G, VR));
     }
-    if (diag_pos >= 0) {
-        val[diag_pos] = diag;
-        if (code) code[diag_pos] = code_base[diag_pos];
+    if (dpos >= 0) {
+        val[dpos] = diag;
+        if (code) code[dpos] = code_base[dpos];
     }
-    if (diag_out) diag_out[r] = diag;
+    if (blobs) reinterpret_cast<double *>(blobs)[diag_pos[r]] = diag;
     rhs[r] = -ksub;  // D*phi = -Ksub (potential_solver.cpp:379,396)
     if (dinv) dinv[r] = 1.0 / diag;
 }
@@ -125,67 +129,71 @@ __global__ void tile_rows_kernel(int m, int num_tiles, const int *__restrict__ r
 // once (one DRAM round trip per tile), gathers x through the read-only path and parks the
 // products in shared memory; phase 2 adds each row's products in CSR order.
 template <int MODE>
-__global__ void __launch_bounds__(kSpmvThreads) spmv_tile_kernel(
-    int m, int nnz, const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
+__global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_kernel(
+    int num_tiles, int nnz, const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
     const double *__restrict__ x, double *__restrict__ y, const int4 *__restrict__ tile_info,
     const double *__restrict__ w, const double *__restrict__ dinv, double *partials, unsigned int *counter,
     double *dot_out, const int *done_flag, int flags) {
     __shared__ __align__(16) double prod[kSpmvCap];
     __shared__ double red[32];
     if (done_flag && *done_flag) return;
-    const int4 ti = tile_info[blockIdx.x];
-    const int r0 = ti.x, r1 = ti.y;
     double local = 0.0;
-    if (r0 < r1) {
-        const int k0 = ti.z, k1 = ti.w;
-        const int ka = k0 & ~1;  // even start: 16-byte aligned double2 / 8-byte aligned int2
-        // row bounds of this thread's first row, requested before the big loads
-        int my_r = r0 + threadIdx.x, ra = 0, rb = 0;
-        if (my_r < r1) { ra = row_ptr[my_r]; rb = row_ptr[my_r + 1]; }
-        if (k1 - ka <= kSpmvCap) {
-            // two batches of four 8-byte/4-byte loads per thread (32 registers -> 8 blocks per SM)
+    // grid-stride over the tiles: at most 6 CTAs per SM worth of partial sums for the fused dot
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int4 ti = tile_info[t];
+        const int r0 = ti.x, r1 = ti.y;
+        if (r0 < r1) {
+            const int k0 = ti.z, k1 = ti.w;
+            const int ka = k0 & ~1;  // even start: 16-byte aligned double2 / 8-byte aligned int2
+            // row bounds of this thread's first row, requested before the big loads
+            int my_r = r0 + threadIdx.x, ra = 0, rb = 0;
+            if (my_r < r1) { ra = row_ptr[my_r]; rb = row_ptr[my_r + 1]; }
+            if (k1 - ka <= kSpmvCap) {
+                // two batches of four 8-byte/4-byte loads per thread (32 registers -> 8 blocks per SM)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                double v[4];
-                int c[4];
+                for (int h = 0; h < 2; ++h) {
+                    double v[4];
+                    int c[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
-                    bool ok = k < k1;
-                    if (flags & 1) {  // keep the matrix in L2 across CG iterations
-                        v[u] = ok ? __ldg(val + k) : 0.0;
-                        c[u] = ok ? __ldg(col + k) : 0;
-                    } else {
-                        v[u] = ok ? __ldcs(val + k) : 0.0;
-                        c[u] = ok ? __ldcs(col + k) : 0;
+                    for (int u = 0; u < 4; ++u) {
+                        int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
+                        bool ok = k < k1;
+                        if (flags & 1) {  // keep the matrix in L2 across CG iterations
+                            v[u] = ok ? __ldg(val + k) : 0.0;
+                            c[u] = ok ? __ldg(col + k) : 0;
+                        } else {
+                            v[u] = ok ? __ldcs(val + k) : 0.0;
+                            c[u] = ok ? __ldcs(col + k) : 0;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
+                        if (k < k1) prod[k - ka] = v[u] * __ldg(x + c[u]);
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
-                    if (k < k1) prod[k - ka] = v[u] * __ldg(x + c[u]);
+                __syncthreads();
+                // phase 2: each row adds its products in CSR order
+                for (int r = my_r; r < r1; r += kSpmvThreads) {
+                    if (r != my_r) { ra = row_ptr[r]; rb = row_ptr[r + 1]; }
+                    double s = 0.0;
+#pragma unroll 4
+                    for (int k = ra - ka; k < rb - ka; ++k) s += prod[k];
+                    if (MODE == 2) { s = w[r] - s; local += s * s * dinv[r]; }
+                    y[r] = s;
+                    if (MODE == 1) local += w[r] * s;
+                }
+            } else {  // rows too long for the staging buffer: direct path
+                for (int r = my_r; r < r1; r += kSpmvThreads) {
+                    double s = 0.0;
+                    for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) s += val[k] * __ldg(x + col[k]);
+                    if (MODE == 2) { s = w[r] - s; local += s * s * dinv[r]; }
+                    y[r] = s;
+                    if (MODE == 1) local += w[r] * s;
                 }
             }
-            __syncthreads();
-            // phase 2: each row adds its products in CSR order
-            for (int r = my_r; r < r1; r += kSpmvThreads) {
-                if (r != my_r) { ra = row_ptr[r]; rb = row_ptr[r + 1]; }
-                double s = 0.0;
-#pragma unroll 4
-                for (int k = ra - ka; k < rb - ka; ++k) s += prod[k];
-                if (MODE == 2) { s = w[r] - s; local += s * s * dinv[r]; }
-                y[r] = s;
-                if (MODE == 1) local += w[r] * s;
-            }
-        } else {  // rows too long for the staging buffer: direct path
-            for (int r = my_r; r < r1; r += kSpmvThreads) {
-                double s = 0.0;
-                for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) s += val[k] * __ldg(x + col[k]);
-                if (MODE == 2) { s = w[r] - s; local += s * s * dinv[r]; }
-                y[r] = s;
-                if (MODE == 1) local += w[r] * s;
-            }
         }
+        __syncthreads();  // prod is reused by the next tile
     }
     if (MODE != 0) {
         double tot = block_sum(local, red);
@@ -686,45 +694,61 @@ static int build_clusters(dkmc_ctx *ctx, int m, int NL, const unsigned char *cls
 static int get_win_format(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const int4 *tile_info,
                           int num_tiles) {
     WinFormat &w = ctx->win;
+    if (!ctx->use_window_spmv) return DKMC_OK;
     if (w.row_ptr == d_row_ptr && w.col == d_col && w.m == m && w.nnz == nnz) return DKMC_OK;
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
     free_win_format(ctx);
-    const int rp_pad = ((m + 1 + 3) & ~3) + 8;
+    // blob sizes follow from the tile extents alone: lay them out on the host
+    std::vector<int4> ti((size_t)num_tiles), plan((size_t)num_tiles);
+    DKMC_CUDA(cudaMemcpy(ti.data(), tile_info, (size_t)num_tiles * sizeof(int4), cudaMemcpyDeviceToHost));
+    size_t off = 0;
+    for (int t = 0; t < num_tiles; ++t) {
+        const int rows = ti[t].y - ti[t].x, n = ti[t].w - ti[t].z;
+        const bool fits = n <= kWinMaxTileNnz && rows <= kWinMaxTileNnz && n >= 0 && rows >= 0;
+        const WinBlob B = win_blob(fits ? rows : 0, fits ? n : 0);
+        plan[t] = make_int4((int)(off / 128), B.bytes, 0, 0);
+        off += (size_t)B.bytes;
+    }
+    if (off / 2 >= 0x7fffffffull) {  // row positions are 32-bit halfword indices
+        w.row_ptr = d_row_ptr; w.col = d_col; w.m = m; w.nnz = nnz; w.num_tiles = num_tiles; w.ok = false;
+        return DKMC_OK;
+    }
+    w.blob_bytes = off;
+    DKMC_CUDA(cudaMalloc(&w.blobs, off + 256));
+    DKMC_CUDA(cudaMalloc(&w.plan, (size_t)num_tiles * sizeof(int4)));
     DKMC_CUDA(cudaMalloc(&w.code_base, ((size_t)nnz + 32) * sizeof(unsigned short)));
-    DKMC_CUDA(cudaMalloc(&w.code, ((size_t)nnz + 32) * sizeof(unsigned short)));
-    DKMC_CUDA(cudaMalloc(&w.rp, (size_t)rp_pad * sizeof(int)));
-    DKMC_CUDA(cudaMalloc(&w.diag, ((size_t)m + 8) * sizeof(double)));
-    DKMC_CUDA(cudaMalloc(&w.hdr, (size_t)num_tiles * sizeof(WinTileHdr)));
-    DKMC_CUDA(cudaMalloc(&w.runs, (size_t)num_tiles * kWinMaxRuns * sizeof(int2)));
-    DKMC_CUDA(cudaMemsetAsync(w.code_base, 0, ((size_t)nnz + 32) * sizeof(unsigned short), ctx->stream));
-    DKMC_CUDA(cudaMemsetAsync(w.code, 0, ((size_t)nnz + 32) * sizeof(unsigned short), ctx->stream));
-    DKMC_CUDA(cudaMemsetAsync(w.diag, 0, ((size_t)m + 8) * sizeof(double), ctx->stream));
-    int *flags;  // fail bits | max chunk
+    DKMC_CUDA(cudaMalloc(&w.code_pos, ((size_t)m + 8) * sizeof(int)));
+    DKMC_CUDA(cudaMalloc(&w.diag_pos, ((size_t)m + 8) * sizeof(int)));
+    DKMC_CUDA(cudaMemsetAsync(w.blobs, 0, off + 256, ctx->stream));
+    DKMC_CUDA(cudaMemcpyAsync(w.plan, plan.data(), (size_t)num_tiles * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+    int *flags;  // fail bits | max staged tile
     int rc;
     if ((rc = ensure<int>(ctx, S_SEL_OUT, 4, &flags))) return rc;
     DKMC_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
-    DKMC_LAUNCH(ctx, win_copy_rowptr_kernel, ceil_div(rp_pad, 256), 256, 0, m, rp_pad, d_row_ptr, w.rp);
-    DKMC_LAUNCH(ctx, win_build_kernel, num_tiles, 256, 0, m, num_tiles, d_row_ptr, d_col, tile_info, w.code_base,
-                static_cast<WinTileHdr *>(w.hdr), static_cast<int2 *>(w.runs), flags, flags + 1);
+    DKMC_LAUNCH(ctx, win_build_kernel, num_tiles, 256, 0, m, num_tiles, d_row_ptr, d_col, tile_info,
+                static_cast<int4 *>(w.plan), w.blobs, w.code_base, w.code_pos, w.diag_pos, flags, flags + 1);
     int h[2] = {0, 0};
     DKMC_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));  // also keeps `plan` alive until the copy is done
     w.row_ptr = d_row_ptr; w.col = d_col; w.m = m; w.nnz = nnz; w.num_tiles = num_tiles;
     w.fail_bits = h[0]; w.max_chunk = h[1];
-    w.ok = (h[0] == 0) && !(g_flags & 32);
+    w.ok = (h[0] == 0);
     w.val_tag = nullptr;
     if (getenv("DKMC_VERBOSE"))
-        fprintf(stderr, "dkmc: window-staged SpMV format: %d tiles, largest staged tile %d bytes, fail bits %d -> %s\n",
-                num_tiles, h[1], h[0], w.ok ? "enabled" : "CSR kernels");
+        fprintf(stderr, "dkmc: window-staged SpMV format: %d tiles, %.1f MB of blobs (%.2f bytes per non-zero), largest staged "
+                "tile %d bytes, fail bits %d -> %s\n", num_tiles, off / 1e6, (double)off / nnz, h[1], h[0],
+                w.ok ? "enabled" : "CSR kernels");
     return DKMC_OK;
 }
 
-// SpMV over `ntiles` tiles starting at `tile_info`.  Three kernels, fastest applicable first:
-//   * window-staged (spmv_win.cuh) when d_val is the matrix the context assembled last and x can be
-//     bulk-copied (64-byte aligned, readable up to the next multiple of 8 entries);
-//   * TMA-fed CSR (spmv_tma.cuh) when val/col are 16-byte aligned;
-//   * register-staged CSR otherwise.
-// All three produce bit-identical y.  x_readable = number of doubles that may be read from d_x.
+// SpMV over `ntiles` tiles starting at `tile_info`.  Three kernels with bit-identical y:
+//   * register-staged CSR (spmv_tile_kernel): the default.  Measured at 1 M sites: 67 us alone (75 % of
+//     the measured HBM peak), CG iteration 111 us;
+//   * TMA-fed CSR (spmv_tma.cuh), DKMC_FLAGS bit 4: 87 us alone, CG iteration 128 us — its three
+//     74 KB rings per SM leave the x gathers almost no L1;
+//   * window-staged (spmv_win.cuh), opt-in through dkmc_ctx_set_window_spmv: 4x fewer DRAM bytes,
+//     73-86 us, bound by shared-memory gathers and instruction issue.
+// x_readable = number of doubles that may be read from d_x (window-staged kernel only).
 template <int MODE>
 static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_row_ptr, const int *d_col,
                        const double *d_val, const double *d_x, double *d_y, const int4 *tile_info, const double *w,
@@ -732,7 +756,7 @@ static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_r
                        const int *done_flag, int x_readable = 0) {
     if (ntiles <= 0) return DKMC_OK;
     const WinFormat &wf = ctx->win;
-    if (wf.ok && wf.row_ptr == d_row_ptr && wf.val_tag == d_val && d_val != nullptr &&
+    if (ctx->use_window_spmv && wf.ok && wf.row_ptr == d_row_ptr && wf.val_tag == d_val && d_val != nullptr &&
         (reinterpret_cast<uintptr_t>(d_x) & 63) == 0 && x_readable >= ((m + 7) & ~7) && (MODE != 1 || w == d_x)) {
         static bool configured = false;
         if (!configured) {
@@ -741,18 +765,42 @@ static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_r
         }
         const int t0 = (int)(tile_info - reinterpret_cast<const int4 *>(ctx->tiling.d_tile_row));
         WinMatrix A;
-        A.code = wf.code; A.rp = wf.rp; A.diag = wf.diag;
-        A.hdr = static_cast<const WinTileHdr *>(wf.hdr) + t0;
-        A.runs = static_cast<const int2 *>(wf.runs) + (size_t)t0 * kWinMaxRuns;
+        A.blobs = wf.blobs;
+        A.plan = static_cast<const int4 *>(wf.plan) + t0;
         A.m_high = wf.m_high; A.m_low = wf.m_low; A.num_tiles = ntiles;
-        int grid = ctx->num_sms < ntiles ? ctx->num_sms : ntiles;
         static const int dbg = [] { const char *e = getenv("DKMC_WIN_DBG"); return e ? atoi(e) : 0; }();
-        DKMC_LAUNCH(ctx, spmv_win_kernel<MODE>, grid, kWinThreads, kWinSmemBytes, A, d_x, d_y, w, dinv, partials, counter,
-                    dot_out, done_flag, dbg);
+        // experiment: DKMC_WIN_CFG="ctas_per_sm,threads,loaders"
+        static int cfg[3] = {1, kWinThreads, kWinLoaders};
+        static bool cfg_read = false;
+        if (!cfg_read) { const char *e = getenv("DKMC_WIN_CFG"); if (e) sscanf(e, "%d,%d,%d", &cfg[0], &cfg[1], &cfg[2]); cfg_read = true; }
+        int ring = ((kWinRingBytes / cfg[0]) / 128) * 128;
+        if (ring < wf.max_chunk) ring = wf.max_chunk;
+        const size_t smem = (size_t)ring + (kWinSmemBytes - kWinRingBytes);
+        int grid = ctx->num_sms * cfg[0];
+        if (grid > ntiles) grid = ntiles;
+        long long *prof = nullptr;
+        if (dbg & 16) {  // per-role wait/total cycle sums (see tools/spmv_experiment.py)
+            int rc;
+            if ((rc = ensure<long long>(ctx, S_SEL_OUT, 8, &prof))) return rc;
+            DKMC_CUDA(cudaMemsetAsync(prof, 0, 8 * sizeof(long long), ctx->stream));
+        }
+        DKMC_LAUNCH(ctx, spmv_win_kernel<MODE>, grid, cfg[1], smem, A, d_x, d_y, w, dinv, partials, counter,
+                    dot_out, done_flag, dbg, ring, cfg[2], prof);
+        if (dbg & 16) {
+            long long h[8];
+            DKMC_CUDA(cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+            static int printed = 0;
+            if (printed++ < 2) {
+                const double nc = grid, nl = (double)grid * cfg[2], nco = (double)grid * (cfg[1] / 32 - 1 - cfg[2]);
+                fprintf(stderr, "win prof (kcycles per warp): producer wait %.1f of %.1f | loader wait %.1f of %.1f | consumer wait %.1f of %.1f\n",
+                        h[0] / nc / 1e3, h[1] / nc / 1e3, h[2] / nl / 1e3, h[3] / nl / 1e3, h[4] / nco / 1e3, h[5] / nco / 1e3);
+            }
+        }
         return DKMC_OK;
     }
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_val) | reinterpret_cast<uintptr_t>(d_col)) & 15) == 0;
-    if (aligned && !(g_flags & 16)) {
+    if (aligned && (g_flags & 16)) {
         static bool configured = false;
         if (!configured) {
             DKMC_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
@@ -765,7 +813,9 @@ static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_r
         DKMC_LAUNCH(ctx, spmv_tma_kernel<MODE>, grid, kTmaThreads, kTmaSmemBytes, ntiles, nnz, d_row_ptr, d_col, d_val, d_x,
                     d_y, tile_info, w, dinv, partials, counter, dot_out, done_flag);
     } else {
-        DKMC_LAUNCH(ctx, spmv_tile_kernel<MODE>, ntiles, kSpmvThreads, 0, m, nnz, d_row_ptr, d_col, d_val, d_x, d_y,
+        int grid = ctx->num_sms * 6;
+        if (MODE == 0 || grid > ntiles) grid = ntiles;  // no dot to finish: one tile per CTA
+        DKMC_LAUNCH(ctx, spmv_tile_kernel<MODE>, grid, kSpmvThreads, 0, ntiles, nnz, d_row_ptr, d_col, d_val, d_x, d_y,
                     tile_info, w, dinv, partials, counter, dot_out, done_flag, g_flags);
     }
     return DKMC_OK;
@@ -1191,10 +1241,17 @@ int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_
                           nullptr, nullptr, nullptr);
 }
 
+int dkmc_ctx_set_window_spmv(dkmc_ctx *ctx, int on) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    ctx->use_window_spmv = on ? 1 : 0;
+    return DKMC_OK;
+}
+
 int dkmc_spmv_window(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                      const double *d_x, int x_readable, double *d_y) {
     DKMC_REQUIRE(ctx && d_row_ptr && d_col && d_val && d_x && d_y, "null pointer");
     const WinFormat &wf = ctx->win;
+    DKMC_REQUIRE(ctx->use_window_spmv, "the window-staged SpMV is switched off: dkmc_ctx_set_window_spmv(ctx, 1)");
     DKMC_REQUIRE(wf.ok && wf.row_ptr == d_row_ptr && wf.val_tag == d_val,
                  "the window-staged format holds another matrix (or this pattern exceeds its limits): call dkmc_assemble_K first");
     DKMC_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 63) == 0 && x_readable >= ((m + 7) & ~7),
@@ -1223,13 +1280,13 @@ int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int N
     if ((rc = get_tiling(ctx, sp->m, sp->nnz, sp->d_row_ptr, &tile_row, &num_tiles))) return rc;
     if ((rc = get_win_format(ctx, sp->m, sp->nnz, sp->d_row_ptr, sp->d_col, tile_row, num_tiles))) return rc;
     WinFormat &wf = ctx->win;
-    const bool win_ok = wf.ok;
+    const bool win_ok = wf.ok && ctx->use_window_spmv && wf.row_ptr == sp->d_row_ptr;
     if (wf.val_tag == d_val) wf.val_tag = nullptr;
     DKMC_LAUNCH(ctx, site_class_kernel, ceil_div(N, 256), 256, 0, N, d_site_element, d_site_charge, d_metals,
                 num_metals, cls);
     DKMC_LAUNCH(ctx, assemble_kernel, ceil_div(sp->m, 128), 128, 0, sp->m, N, NL, NR, Vd, high_G, low_G, cls,
                 sp->d_row_ptr, sp->d_col, sp->d_left_row_ptr, sp->d_left_col, sp->d_right_row_ptr, sp->d_right_col,
-                d_val, d_rhs, dinv, win_ok ? wf.code_base : nullptr, win_ok ? wf.code : nullptr, win_ok ? wf.diag : nullptr);
+                d_val, d_rhs, dinv, wf.code_base, wf.code_pos, wf.diag_pos, win_ok ? wf.blobs : nullptr);
     if (win_ok) { wf.val_tag = d_val; wf.m_high = -high_G; wf.m_low = -low_G; }
     return DKMC_OK;
 }

@@ -45,6 +45,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// same, but lets the hardware park the thread (up to ~`hint_ns`) instead of re-polling: a spinning
+// lane otherwise takes issue slots from the warps that do the arithmetic
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity, uint32_t hint_ns = 20000u) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),

@@ -134,7 +134,10 @@ int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_
  * off-diagonal values and a static pattern, so dkmc_assemble_K also keeps a window-staged form of
  * the matrix it assembled last (2 bytes per non-zero, x pieces bulk-copied to shared memory).  d_val
  * must be that matrix; d_x 64-byte aligned with x_readable >= m rounded up to 8 readable entries.
- * Bit-identical to dkmc_spmv.  DKMC_ERR_ARG if the pattern exceeds the format's limits. */
+ * Bit-identical to dkmc_spmv.  DKMC_ERR_ARG if the pattern exceeds the format's limits.
+ * EXPERIMENTAL and off by default: it moves 4x fewer DRAM bytes but is bound by shared-memory
+ * gathers and instruction issue, and is not faster than the CSR kernels inside the CG yet. */
+int dkmc_ctx_set_window_spmv(dkmc_ctx *ctx, int on); /* default off (experimental) */
 int dkmc_spmv_window(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
                      const double *d_val, const double *d_x, int x_readable, double *d_y);
 int dkmc_solve_cg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
@@ -168,8 +171,8 @@ int dkmc_poisson_gridless_begin(dkmc_ctx *ctx, int pbc, int N, const double *d_l
                                 const double *d_y, const double *d_z, const int *d_site_charge,
                                 int row_begin, int row_end, double *d_site_potential_charge);
 int dkmc_poisson_gridless_join(dkmc_ctx *ctx, double *pairwise_ms);
-/* CTAs per SM the overlapped pairwise kernel may occupy (default 6 of the 10 that fit) */
-int dkmc_ctx_set_pairwise_share(dkmc_ctx *ctx, int blocks_per_sm);
+/* share of each SM the overlapped pairwise kernel may occupy: CTAs per SM x threads per CTA */
+int dkmc_ctx_set_pairwise_share(dkmc_ctx *ctx, int blocks_per_sm, int threads_per_block);
 
 /* ---- a7: rate table.  build_event_list, kmc_events.cu:34-126 with the CPU semantics of
  * KMCProcess::update_events_and_rates, KMCProcess.cpp:67-164 (vacancy-diffusion barrier from

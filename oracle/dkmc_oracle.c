@@ -599,6 +599,11 @@ static void apply_event(int type, int i, int j, int *element, int *charge) {
     }
 }
 
+/* benchmark aid (bench.py's bounded CPU sample): stop the residence-time loop after this many
+ * executed events; 0 = run the step to its end as the reference does */
+static int g_event_limit = 0;
+void orc_set_event_limit(int n) { g_event_limit = n > 0 ? n : 0; }
+
 int orc_kmc_events(int N, int nn, const int *neigh_idx, int *event_type, double *event_prob,
                    int *element, int *charge, double freq, orc_rng *rng, double *event_time_out,
                    int *events, int max_events) {
@@ -614,6 +619,7 @@ int orc_kmc_events(int N, int nn, const int *neigh_idx, int *event_type, double 
     double event_time = 0.0;
     int ne = 0;
     while (event_time < 1 / freq) {
+        if (g_event_limit > 0 && ne >= g_event_limit) break;
         long live = 0;
         double acc = 0.0;
         for (long t = 0; t < nz; ++t) {

@@ -113,6 +113,7 @@ double orc_rng_uniform(orc_rng *r);
  * (KMCProcess.cpp:187-256), conflict zeroing (330-352), event_time = -log(u)/Psum.
  * events[4*e + {0,1,2,3}] = table idx, i, j, type.  Returns #events (may exceed max_events;
  * only the first max_events are recorded).  event_type/event_prob are modified in place. */
+void orc_set_event_limit(int n);
 int orc_kmc_events(int N, int nn, const int *neigh_idx, int *event_type, double *event_prob,
                    int *element, int *charge, double freq, orc_rng *rng, double *event_time,
                    int *events, int max_events);

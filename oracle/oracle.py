@@ -183,6 +183,11 @@ def kmc_events(neigh_idx, event_type, event_prob, element, charge, freq, rng: Rn
     return t.value, ev[: 4 * min(ne, max_events)].reshape(-1, 4).copy(), el, q
 
 
+def set_event_limit(n: int):
+    """bench.py only: stop kmc_events after n executed events (0 = no limit)"""
+    lib().orc_set_event_limit(int(n))
+
+
 def select_event(event_prob, u):
     ep = _f64(event_prob)
     ps = C.c_double(0.0)

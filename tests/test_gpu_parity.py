@@ -431,6 +431,7 @@ def test_spmv_window_bit_identical_to_csr(cell_sim, torch):
     from devicekmc_b200._capi import check
     p, dev, sim, buf, nc = cell_sim
     lib = dev.ctx.lib
+    check(lib.dkmc_ctx_set_window_spmv(dev.ctx.h, 1))
     sp = buf.sparsity(nc, nc)
     val = torch.zeros(sp.nnz, dtype=torch.float64, device="cuda")
     rhs = torch.zeros(sp.m, dtype=torch.float64, device="cuda")
@@ -455,6 +456,14 @@ def test_spmv_window_bit_identical_to_csr(cell_sim, torch):
     st = lib.dkmc_spmv_window(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, other.data_ptr(), xfull.data_ptr(), pad,
                               y_win.data_ptr())
     assert st == 2  # DKMC_ERR_ARG
+    # the CG through the window-staged kernel reproduces the CSR-kernel solution bit for bit
+    buf.site_potential_boundary.zero_()
+    dev.updatePotential(buf, p, 10.0, n_contact=nc, overlap=False)
+    b_win = buf.site_potential_boundary.clone()
+    check(lib.dkmc_ctx_set_window_spmv(dev.ctx.h, 0))
+    buf.site_potential_boundary.zero_()
+    dev.updatePotential(buf, p, 10.0, n_contact=nc, overlap=False)
+    assert float((b_win - buf.site_potential_boundary).abs().max()) <= 1e-13 * float(b_win.abs().max())
 
 
 def test_potential_overlap_matches_serial(cell_sim, O, torch):
