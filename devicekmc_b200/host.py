@@ -388,35 +388,34 @@ class GPUBuffers:
             self._sparsity[key] = sp
         return self._sparsity[key]
 
-    def _pinned(self, name, arr):
+    _SYNCED = ("site_element", "site_charge", "site_potential_boundary", "site_potential_charge", "site_temperature")
+
+    def _pinned(self, device: Device, name: str):
+        """The host array `device.<name>` re-homed (once) in page-locked memory, so that the syncs are
+        plain DMA transfers with no staging copy: returns the pinned tensor that shares its storage."""
         torch = _torch()
-        if name not in self._pin:
-            self._pin[name] = torch.empty(arr.shape, dtype=torch.from_numpy(arr).dtype).pin_memory()
-        return self._pin[name]
+        arr = getattr(device, name)
+        ent = self._pin.get(name)
+        if ent is None or ent[1] is not arr:
+            t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+            view = t.numpy()
+            setattr(device, name, view)
+            ent = (t, view)
+            self._pin[name] = ent
+        return ent[0]
 
     def sync_HostToGPU(self, device: Device):
         """gpu_buffers.cpp:10-37"""
-        torch = _torch()
-        for name in ("site_element", "site_charge", "site_potential_boundary", "site_potential_charge",
-                     "site_temperature"):
-            src = getattr(device, name)
-            pin = self._pinned(name, src)
-            pin.copy_(torch.from_numpy(src))
-            getattr(self, name).copy_(pin, non_blocking=True)
+        for name in self._SYNCED:
+            getattr(self, name).copy_(self._pinned(device, name), non_blocking=True)
         self.T_bg.fill_(device.T_bg)
 
     def sync_GPUToHost(self, device: Device):
         """gpu_buffers.cpp:39-55"""
         torch = _torch()
-        for name in ("site_element", "site_charge", "site_potential_boundary", "site_potential_charge",
-                     "site_temperature"):
-            dst = getattr(device, name)
-            pin = self._pinned(name, dst)
-            pin.copy_(getattr(self, name), non_blocking=True)
+        for name in self._SYNCED:
+            self._pinned(device, name).copy_(getattr(self, name), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        for name in ("site_element", "site_charge", "site_potential_boundary", "site_potential_charge",
-                     "site_temperature"):
-            getattr(device, name)[...] = self._pin[name].numpy()
 
     def h2d_bytes(self) -> int:
         return self.N_ * (4 + 4 + 8 + 8 + 8)

@@ -179,11 +179,11 @@ def bench_multi_gpu(args, metric: str, unit: str):
     el = bench.substoichiometric(el, p)
     s = SlabSim((el, x, y, z), p, rank, world, distributed_cg=not args.replicated_cg)
     stats = []
-    for _ in range(args.warmup):
-        s.step(args.vd)
     sampler = bench.ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(args.warmup):
+        s.step(args.vd)
     launches0 = s.dev.ctx.launch_count()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
