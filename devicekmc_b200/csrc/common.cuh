@@ -51,7 +51,7 @@ enum Slot : int {
     S_SP_CNT, S_SCAN_BLOCK,
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
-    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR,
+    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_PCOL, S_CG_PDIAG,
     S_LAST
 };
 static_assert(S_LAST <= kNumSlots, "increase kNumSlots");
@@ -79,6 +79,15 @@ struct WinFormat {
     double m_high = 0.0, m_low = 0.0;    // -high_G, -low_G
 };
 
+// packed CSR of the matrix the context assembled last (solver.cu): 4 bytes per non-zero
+struct PackedCsr {
+    int *pcol = nullptr;               // column | bit 31 high_G | bit 30 diagonal
+    double *diag = nullptr;            // per-row diagonal of K
+    const int *row_ptr = nullptr;      // the pattern it belongs to
+    const double *val_tag = nullptr;   // the CSR values it mirrors
+    double m_high = 0.0, m_low = 0.0;  // -high_G, -low_G
+};
+
 }  // namespace dkmc
 
 struct dkmc_ctx {
@@ -99,6 +108,8 @@ struct dkmc_ctx {
     } grid;
     dkmc::SpmvTiling tiling;
     dkmc::WinFormat win;
+    dkmc::PackedCsr packed;
+    int use_packed_spmv = 0;   // opt-in (dkmc_ctx_set_packed_spmv): measured no faster, the SpMV is gather-bound
     int use_window_spmv = 0;   // opt-in (dkmc_ctx_set_window_spmv / DKMC_WINDOW_SPMV=1)
     // event loop state for dkmc_kmc_step_continue
     struct {

@@ -101,6 +101,7 @@ int dkmc_ctx_create(dkmc_ctx **out) {
     DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     DKMC_CUDA(cudaEventCreate(&ctx->ev_pw0));
     DKMC_CUDA(cudaEventCreate(&ctx->ev_pw1));
+    if (const char *e = getenv("DKMC_PACKED_SPMV")) ctx->use_packed_spmv = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DKMC_WINDOW_SPMV")) ctx->use_window_spmv = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DKMC_PW_SIDE_BPS")) { int v = atoi(e); if (v > 0) ctx->pw_side_blocks_per_sm = v; }
     *out = ctx;

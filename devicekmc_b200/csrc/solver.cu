@@ -42,6 +42,12 @@ struct CgScalars {
     unsigned int cnt_a, cnt_b, cnt_c, cnt_d;
 };
 
+// Packed CSR of K for the CG's SpMV: K has two distinct off-diagonal values (-high_G, -low_G), so the
+// assembly also writes, per non-zero, the column with the choice in bit 31 (and bit 30 on the diagonal,
+// whose value lives in a per-row array).  The SpMV then streams 4 bytes per non-zero instead of 12
+// and forms the very same products, hence bit-identical results.
+constexpr int kPackHigh = (int)0x80000000u, kPackDiag = 0x40000000, kPackMask = 0x3fffffff;
+
 // ---------------------------------------------------------------- site class + assembly
 __global__ void site_class_kernel(int N, const int *__restrict__ element, const int *__restrict__ charge,
                                   const int *__restrict__ metals, int num_metals,
@@ -65,7 +71,8 @@ __global__ void __launch_bounds__(128) assemble_kernel(
     const int *__restrict__ lrp, const int *__restrict__ lcol, const int *__restrict__ rrp,
     const int *__restrict__ rcol, double *__restrict__ val, double *__restrict__ rhs,
     double *__restrict__ dinv, const unsigned short *__restrict__ code_base, const int *__restrict__ code_pos,
-    const int *__restrict__ diag_pos, unsigned char *__restrict__ blobs) {
+    const int *__restrict__ diag_pos, unsigned char *__restrict__ blobs, int *__restrict__ pcol,
+    double *__restrict__ pdiag) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     const double VL = -Vd / 2, VR = Vd / 2;
@@ -87,6 +94,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(
         const unsigned char cj = cls[c + NL];
         double G = conductance(ci, cj, high_G, low_G);
         val[p] = -G;
+        if (pcol) pcol[p] = c | ((ci != 0 && ci == cj) ? kPackHigh : 0);           // packed CSR: column | high_G bit
         if (code) code[p] = code_base[p] | ((ci != 0 && ci == cj) ? 0x4000 : 0);  // window-staged format: high_G bit
         diag = __dadd_rn(diag, G);
     }
@@ -97,8 +105,10 @@ __global__ void __launch_bounds__(128) assemble_kernel(
     }
     if (dpos >= 0) {
         val[dpos] = diag;
+        if (pcol) pcol[dpos] = r | kPackDiag;
         if (code) code[dpos] = code_base[dpos];
     }
+    if (pdiag) pdiag[r] = diag;
     if (blobs) reinterpret_cast<double *>(blobs)[diag_pos[r]] = diag;
     rhs[r] = -ksub;  // D*phi = -Ksub (potential_solver.cpp:379,396)
     if (dinv) dinv[r] = 1.0 / diag;
@@ -128,12 +138,14 @@ __global__ void tile_rows_kernel(int m, int num_tiles, const int *__restrict__ r
 // Phase 1 streams the tile's val/col with 16-byte loads, all 8 elements of a thread in flight at
 // once (one DRAM round trip per tile), gathers x through the read-only path and parks the
 // products in shared memory; phase 2 adds each row's products in CSR order.
-template <int MODE>
+// PACKED: `col` holds the packed columns, `val` the per-row diagonal, (m_high, m_low) the two
+// off-diagonal values.
+template <int MODE, bool PACKED = false>
 __global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_kernel(
     int num_tiles, int nnz, const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
     const double *__restrict__ x, double *__restrict__ y, const int4 *__restrict__ tile_info,
     const double *__restrict__ w, const double *__restrict__ dinv, double *partials, unsigned int *counter,
-    double *dot_out, const int *done_flag, int flags) {
+    double *dot_out, const int *done_flag, int flags, double m_high = 0.0, double m_low = 0.0) {
     __shared__ __align__(16) double prod[kSpmvCap];
     __shared__ double red[32];
     if (done_flag && *done_flag) return;
@@ -158,7 +170,9 @@ __global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_ker
                     for (int u = 0; u < 4; ++u) {
                         int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
                         bool ok = k < k1;
-                        if (flags & 1) {  // keep the matrix in L2 across CG iterations
+                        if (PACKED) {
+                            c[u] = ok ? __ldcs(col + k) : 0;
+                        } else if (flags & 1) {  // keep the matrix in L2 across CG iterations
                             v[u] = ok ? __ldg(val + k) : 0.0;
                             c[u] = ok ? __ldg(col + k) : 0;
                         } else {
@@ -169,7 +183,14 @@ __global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_ker
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
-                        if (k < k1) prod[k - ka] = v[u] * __ldg(x + c[u]);
+                        if (PACKED) {
+                            const int cc = c[u] & kPackMask;
+                            const double xv = __ldg(x + cc);
+                            const double vv = (c[u] & kPackDiag) ? __ldg(val + cc) : (c[u] < 0 ? m_high : m_low);
+                            if (k < k1) prod[k - ka] = vv * xv;
+                        } else if (k < k1) {
+                            prod[k - ka] = v[u] * __ldg(x + c[u]);
+                        }
                     }
                 }
                 __syncthreads();
@@ -186,7 +207,14 @@ __global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_ker
             } else {  // rows too long for the staging buffer: direct path
                 for (int r = my_r; r < r1; r += kSpmvThreads) {
                     double s = 0.0;
-                    for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) s += val[k] * __ldg(x + col[k]);
+                    for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+                        if (PACKED) {
+                            const int pc = col[k], cc = pc & kPackMask;
+                            s += ((pc & kPackDiag) ? val[cc] : (pc < 0 ? m_high : m_low)) * __ldg(x + cc);
+                        } else {
+                            s += val[k] * __ldg(x + col[k]);
+                        }
+                    }
                     if (MODE == 2) { s = w[r] - s; local += s * s * dinv[r]; }
                     y[r] = s;
                     if (MODE == 1) local += w[r] * s;
@@ -799,6 +827,14 @@ static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_r
         }
         return DKMC_OK;
     }
+    const PackedCsr &pk = ctx->packed;
+    if (ctx->use_packed_spmv && pk.pcol && pk.row_ptr == d_row_ptr && pk.val_tag == d_val && d_val != nullptr) {
+        int grid = ctx->num_sms * 6;
+        if (MODE == 0 || grid > ntiles) grid = ntiles;
+        DKMC_LAUNCH(ctx, (spmv_tile_kernel<MODE, true>), grid, kSpmvThreads, 0, ntiles, nnz, d_row_ptr, pk.pcol, pk.diag, d_x,
+                    d_y, tile_info, w, dinv, partials, counter, dot_out, done_flag, g_flags, pk.m_high, pk.m_low);
+        return DKMC_OK;
+    }
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_val) | reinterpret_cast<uintptr_t>(d_col)) & 15) == 0;
     if (aligned && (g_flags & 16)) {
         static bool configured = false;
@@ -1241,6 +1277,13 @@ int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_
                           nullptr, nullptr, nullptr);
 }
 
+int dkmc_ctx_set_packed_spmv(dkmc_ctx *ctx, int on) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    ctx->use_packed_spmv = on ? 1 : 0;
+    if (!on) ctx->packed.val_tag = nullptr;
+    return DKMC_OK;
+}
+
 int dkmc_ctx_set_window_spmv(dkmc_ctx *ctx, int on) {
     DKMC_REQUIRE(ctx != nullptr, "ctx");
     ctx->use_window_spmv = on ? 1 : 0;
@@ -1282,12 +1325,21 @@ int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int N
     WinFormat &wf = ctx->win;
     const bool win_ok = wf.ok && ctx->use_window_spmv && wf.row_ptr == sp->d_row_ptr;
     if (wf.val_tag == d_val) wf.val_tag = nullptr;
+    PackedCsr &pk = ctx->packed;
+    pk.val_tag = nullptr;
+    pk.pcol = nullptr;
+    if (ctx->use_packed_spmv && sp->m < kPackDiag) {
+        if ((rc = ensure<int>(ctx, S_CG_PCOL, (size_t)sp->nnz, &pk.pcol))) return rc;
+        if ((rc = ensure<double>(ctx, S_CG_PDIAG, (size_t)sp->m, &pk.diag))) return rc;
+    }
     DKMC_LAUNCH(ctx, site_class_kernel, ceil_div(N, 256), 256, 0, N, d_site_element, d_site_charge, d_metals,
                 num_metals, cls);
     DKMC_LAUNCH(ctx, assemble_kernel, ceil_div(sp->m, 128), 128, 0, sp->m, N, NL, NR, Vd, high_G, low_G, cls,
                 sp->d_row_ptr, sp->d_col, sp->d_left_row_ptr, sp->d_left_col, sp->d_right_row_ptr, sp->d_right_col,
-                d_val, d_rhs, dinv, wf.code_base, wf.code_pos, wf.diag_pos, win_ok ? wf.blobs : nullptr);
+                d_val, d_rhs, dinv, wf.code_base, wf.code_pos, wf.diag_pos, win_ok ? wf.blobs : nullptr, pk.pcol,
+                pk.pcol ? pk.diag : nullptr);
     if (win_ok) { wf.val_tag = d_val; wf.m_high = -high_G; wf.m_low = -low_G; }
+    if (pk.pcol) { pk.val_tag = d_val; pk.row_ptr = sp->d_row_ptr; pk.m_high = -high_G; pk.m_low = -low_G; }
     return DKMC_OK;
 }
 

@@ -128,6 +128,11 @@ class SlabSim:
         self.i1 = min(N, (rank + 1) * self.chunk)
         self.buf.sync_HostToGPU(self.dev)
         self.sp = self.buf.sparsity(self.nc, self.nc)
+        # the pairwise kernel's share of each SM while it runs beside the CG: the fewer targets a rank
+        # owns, the smaller the share it needs to finish before the CG does
+        share = (3, 128) if world == 1 else ((2, 128) if world == 2 else (1, 128))
+        from ._capi import check
+        check(self.dev.ctx.lib.dkmc_ctx_set_pairwise_share(self.dev.ctx.h, share[0], share[1]))
         self.dcg = None
         if distributed_cg and world > 1:
             from . import _dist
@@ -177,7 +182,7 @@ def bench_multi_gpu(args, metric: str, unit: str):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     el, x, y, z, lat, nc, p = bench.workload(args.workload)
     el = bench.substoichiometric(el, p)
-    s = SlabSim((el, x, y, z), p, rank, world, distributed_cg=not args.replicated_cg)
+    s = SlabSim((el, x, y, z), p, rank, world, distributed_cg=bool(getattr(args, 'distributed_cg', False)))
     stats = []
     sampler = bench.ClockSampler(local) if rank == 0 else None
     if sampler:

@@ -130,7 +130,14 @@ int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int N
 /* y = A x, CSR FP64/int32 (replaces cusparseSpMV, iterative_solvers_gpu.cu:411,428) */
 int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
               const double *d_val, const double *d_x, double *d_y);
-/* The same product by the kernel the CG of dkmc_background_potential_sparse uses: K has two distinct
+/* K has only two distinct off-diagonal values (-high_G, -low_G): dkmc_assemble_K also writes a PACKED
+ * form of the matrix it assembled last (int32 column with the choice in bit 31, the diagonal in a
+ * per-row array): 4 bytes per non-zero instead of 12.  dkmc_spmv / the CG use it whenever d_val is
+ * that matrix; the products and their order are the same, so y is bit-identical.  Default OFF:
+ * measured at 1 M sites it is no faster (70.6 us against 65.7 us) — the SpMV is bound by the
+ * 26 M gathers of x through L1/L2, not by the 12 bytes per non-zero it streams from DRAM. */
+int dkmc_ctx_set_packed_spmv(dkmc_ctx *ctx, int on);
+/* An experimental third form of the same product: K has two distinct
  * off-diagonal values and a static pattern, so dkmc_assemble_K also keeps a window-staged form of
  * the matrix it assembled last (2 bytes per non-zero, x pieces bulk-copied to shared memory).  d_val
  * must be that matrix; d_x 64-byte aligned with x_readable >= m rounded up to 8 readable entries.

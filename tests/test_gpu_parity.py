@@ -432,6 +432,7 @@ def test_spmv_window_bit_identical_to_csr(cell_sim, torch):
     p, dev, sim, buf, nc = cell_sim
     lib = dev.ctx.lib
     check(lib.dkmc_ctx_set_window_spmv(dev.ctx.h, 1))
+    check(lib.dkmc_ctx_set_packed_spmv(dev.ctx.h, 1))
     sp = buf.sparsity(nc, nc)
     val = torch.zeros(sp.nnz, dtype=torch.float64, device="cuda")
     rhs = torch.zeros(sp.m, dtype=torch.float64, device="cuda")
@@ -445,8 +446,15 @@ def test_spmv_window_bit_identical_to_csr(cell_sim, torch):
         xfull = torch.full((pad,), float("nan"), dtype=torch.float64, device="cuda")  # padding must never be used
         xfull[:sp.m] = torch.randn(sp.m, dtype=torch.float64, device="cuda", generator=g)
         y_csr = torch.empty(sp.m, dtype=torch.float64, device="cuda")
+        y_pk = torch.full((sp.m,), 5.0, dtype=torch.float64, device="cuda")
         y_win = torch.full((sp.m,), 7.0, dtype=torch.float64, device="cuda")
-        check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xfull.data_ptr(), y_csr.data_ptr()))
+        # packed CSR (4 bytes per non-zero, what the CG streams) vs plain CSR (a copy of the values is not
+        # "the matrix assembled last", so it goes through the val/col kernel)
+        check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xfull.data_ptr(), y_pk.data_ptr()))
+        vcopy = val.clone()
+        check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, vcopy.data_ptr(), xfull.data_ptr(), y_csr.data_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(y_csr, y_pk)
         check(lib.dkmc_spmv_window(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xfull.data_ptr(), pad,
                                    y_win.data_ptr()))
         torch.cuda.synchronize()
@@ -461,6 +469,7 @@ def test_spmv_window_bit_identical_to_csr(cell_sim, torch):
     dev.updatePotential(buf, p, 10.0, n_contact=nc, overlap=False)
     b_win = buf.site_potential_boundary.clone()
     check(lib.dkmc_ctx_set_window_spmv(dev.ctx.h, 0))
+    check(lib.dkmc_ctx_set_packed_spmv(dev.ctx.h, 0))
     buf.site_potential_boundary.zero_()
     dev.updatePotential(buf, p, 10.0, n_contact=nc, overlap=False)
     assert float((b_win - buf.site_potential_boundary).abs().max()) <= 1e-13 * float(b_win.abs().max())

@@ -22,8 +22,12 @@ def timeit(f, reps=50):
     for _ in range(reps): f()
     e1.record(); e1.synchronize()
     return e0.elapsed_time(e1) / reps
-csr = lambda: check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xw.data_ptr(), y1.data_ptr()))
+vcopy = val.clone(); y0 = torch.empty_like(y1)
+csr = lambda: check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, vcopy.data_ptr(), xw.data_ptr(), y0.data_ptr()))
+pk = lambda: check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xw.data_ptr(), y1.data_ptr()))
 win = lambda: check(lib.dkmc_spmv_window(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xw.data_ptr(), pad, y2.data_ptr()))
 B = 12.0 * sp.nnz + 20.0 * sp.m
 t = timeit(csr); print("csr    %.1f us  contract %.0f GB/s" % (t * 1e3, B / t / 1e6))
+t = timeit(pk); print("packed %.1f us  contract %.0f GB/s  actual-bytes %.0f GB/s  identical %s" % (t * 1e3, B / t / 1e6, (4.0 * sp.nnz + 28.0 * sp.m) / t / 1e6, bool(torch.equal(y0, y1))))
+if os.environ.get("DKMC_WINDOW_SPMV") != "1": sys.exit(0)
 t = timeit(win); print("window %.1f us  contract %.0f GB/s  identical %s  dbg=%s" % (t * 1e3, B / t / 1e6, bool(torch.equal(y1, y2)), os.environ.get("DKMC_WIN_DBG", "0")))
