@@ -275,7 +275,11 @@ def gpu_arm(args):
                                         buf.site_charge.data_ptr(), buf.site_potential_charge.data_ptr()))
     e1.record(); e1.synchronize()
     pair_ms = e0.elapsed_time(e1) / 3
-    pairs = float(dev.N) * ncharged - ncharged
+    pairs_total = float(dev.N) * ncharged - ncharged
+    pe = C.c_longlong(-1)
+    check(lib.dkmc_pairwise_pairs_evaluated(dev.ctx.h, C.byref(pe)))
+    # the cell-list kernel skips the pairs whose erfc factor is exactly 0 (r > 131 A): count the rest
+    pairs = float(pe.value) if pe.value > 0 else pairs_total
     pair_tflops = 200.0 * pairs / (pair_ms * 1e-3) / 1e12
     # scan primitive over the N*nn rate table
     n_tab = dev.N * buf.nn_
@@ -303,7 +307,8 @@ def gpu_arm(args):
                  "traffic": None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "peak_source": peak_src},
         "pairwise": {"bound": "fp64", "achieved": pair_tflops, "peak": fp64.value, "unit": "TFLOP/s",
                      "frac": pair_tflops / fp64.value if fp64.value else None, "traffic": None,
-                     "flops_per_pair": 200, "pairs": pairs, "ms_per_launch": pair_ms,
+                     "flops_per_pair": 200, "pairs": pairs, "pairs_all": pairs_total,
+                     "pairs_skipped_exact_zero": 1.0 - pairs / pairs_total, "ms_per_launch": pair_ms,
                      "peak_source": "measured here: DFMA-chain probe (dkmc_probe_fp64_tflops)"},
         "rate_table": {"bound": "hbm", "achieved": 16.0 * n_tab / (rate_ms * 1e-3) / 1e9, "peak": hbm_peak,
                        "unit": "GB/s", "frac": 16.0 * n_tab / (rate_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},

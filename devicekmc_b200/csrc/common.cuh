@@ -51,7 +51,7 @@ enum Slot : int {
     S_SP_CNT, S_SCAN_BLOCK,
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
-    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_PCOL, S_CG_PDIAG,
+    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_PCOL, S_CG_PDIAG, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
     S_LAST
 };
 static_assert(S_LAST <= kNumSlots, "increase kNumSlots");
@@ -135,6 +135,8 @@ struct dkmc_ctx {
         const int *d_charge = nullptr;
         double *d_out = nullptr;
     } pw_pending;
+    int pw_use_cells = 1;            // skip sources beyond the distance where erfc is exactly 0 (non-periodic devices)
+    struct { const double *d_x = nullptr, *d_sigma = nullptr; const void *box = nullptr; int N = 0; } pw_grid;
     int pw_side_threads = 128;
     int pw_side_blocks_per_sm = 3;   // residency of the pairwise kernel while it shares the SMs with the CG
 };
