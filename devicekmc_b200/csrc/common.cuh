@@ -136,7 +136,8 @@ struct dkmc_ctx {
         double *d_out = nullptr;
     } pw_pending;
     int pw_use_cells = 1;            // skip sources beyond the distance where erfc is exactly 0 (non-periodic devices)
-    struct { const double *d_x = nullptr, *d_sigma = nullptr; const void *box = nullptr; int N = 0; } pw_grid;
+    struct { const double *d_x = nullptr, *d_sigma = nullptr; const void *box = nullptr; int N = 0; double cutoff_sigmas = 0.0; } pw_grid;
+    double pw_cutoff_sigmas = 0.0;   // 0: exact; > 0: truncate the pairwise sum at this many sigma (opt-in)
     int pw_side_threads = 128;
     int pw_side_blocks_per_sm = 3;   // residency of the pairwise kernel while it shares the SMs with the CG
 };

@@ -251,12 +251,14 @@ __global__ void __launch_bounds__(256) pw_bbox_partial_kernel(int N, const doubl
 }
 
 __global__ void pw_grid_setup_kernel(int nblocks, const double *__restrict__ part, const double *__restrict__ sigma_ptr,
-                                     PwGrid *g) {
+                                     double cutoff_sigmas, PwGrid *g) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int b = 0; b < nblocks; ++b)
         for (int a = 0; a < 3; ++a) { lo[a] = fmin(lo[a], part[b * 6 + a]); hi[a] = fmax(hi[a], part[b * 6 + 3 + a]); }
-    const double rc = kErfcZero * (*sigma_ptr) * sqrt(2.0) * 1e10 * (1.0 + 1e-12);  // Angstrom, rounded up
+    // exact: the distance beyond which erfc_fast is 0.  cutoff_sigmas > 0: the caller's (shorter) cutoff
+    double rc = kErfcZero * (*sigma_ptr) * sqrt(2.0) * 1e10 * (1.0 + 1e-12);  // Angstrom, rounded up
+    if (cutoff_sigmas > 0.0) rc = fmin(rc, cutoff_sigmas * (*sigma_ptr) * 1e10);
     static_assert(kPwCellsPerCutoff >= 1, "cells per cutoff");
     double h = rc / kPwCellsPerCutoff;
     int n[3];
@@ -493,11 +495,11 @@ static int pairwise_bin_cells(dkmc_ctx *ctx, int N, const double *d_x, const dou
     unsigned long long *pair_counter = reinterpret_cast<unsigned long long *>(box + 6 * kBoxBlocks + (sizeof(PwGrid) + 7) / 8);
     int *cell_count = cells, *cell_start = cells + (kPwMaxCells + 1), *cell_of = cells + 2 * (kPwMaxCells + 1);
     auto &gc = ctx->pw_grid;
-    if (gc.d_x != d_x || gc.d_sigma != d_sigma || gc.N != N || gc.box != box) {
+    if (gc.d_x != d_x || gc.d_sigma != d_sigma || gc.N != N || gc.box != box || gc.cutoff_sigmas != ctx->pw_cutoff_sigmas) {
         // positions are static: the box of the sites and the grid are computed once
         DKMC_LAUNCH(ctx, pw_bbox_partial_kernel, kBoxBlocks, 256, 0, N, d_x, d_y, d_z, box);
-        DKMC_LAUNCH(ctx, pw_grid_setup_kernel, 1, 32, 0, kBoxBlocks, box, d_sigma, grid);
-        gc.d_x = d_x; gc.d_sigma = d_sigma; gc.N = N; gc.box = box;
+        DKMC_LAUNCH(ctx, pw_grid_setup_kernel, 1, 32, 0, kBoxBlocks, box, d_sigma, ctx->pw_cutoff_sigmas, grid);
+        gc.d_x = d_x; gc.d_sigma = d_sigma; gc.N = N; gc.box = box; gc.cutoff_sigmas = ctx->pw_cutoff_sigmas;
     }
     DKMC_CUDA(cudaMemsetAsync(cell_count, 0, (kPwMaxCells + 1) * sizeof(int), ctx->stream));
     DKMC_CUDA(cudaMemsetAsync(pair_counter, 0, sizeof(unsigned long long), ctx->stream));
@@ -671,6 +673,12 @@ int dkmc_poisson_gridless(dkmc_ctx *ctx, int pbc, int N, const double *d_lattice
 int dkmc_ctx_set_pairwise_cells(dkmc_ctx *ctx, int on) {
     DKMC_REQUIRE(ctx != nullptr, "ctx");
     ctx->pw_use_cells = on ? 1 : 0;
+    return DKMC_OK;
+}
+
+int dkmc_ctx_set_pairwise_cutoff(dkmc_ctx *ctx, double cutoff_sigmas) {
+    DKMC_REQUIRE(ctx != nullptr && cutoff_sigmas >= 0.0, "ctx / cutoff_sigmas >= 0");
+    ctx->pw_cutoff_sigmas = cutoff_sigmas;
     return DKMC_OK;
 }
 

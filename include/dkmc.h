@@ -184,6 +184,12 @@ int dkmc_poisson_gridless_join(dkmc_ctx *ctx, double *pairwise_ms);
  * at 1 M sites 56 % of the pairs are skipped.  Periodic devices (pbc = 1) always take the all-pairs
  * kernel.  dkmc_pairwise_pairs_evaluated: pairs the last cell-list sum evaluated (-1: none yet). */
 int dkmc_ctx_set_pairwise_cells(dkmc_ctx *ctx, int on);
+/* OPT-IN approximation, default 0 = off: truncate the sum at cutoff_sigmas * sigma.
+ * erfc(r / (sigma sqrt 2)) < 1.6e-23 beyond 10 sigma, so phi_c changes by < 1e-21 of its largest
+ * entries (far below the 1e-10 parity bound; sites whose every charge is farther away get exactly 0
+ * instead of ~1e-25 V).  This changes the WORK of a6 (70x fewer pairs at 1 M sites); bench.py reports
+ * it as a separate variant, never as the headline. */
+int dkmc_ctx_set_pairwise_cutoff(dkmc_ctx *ctx, double cutoff_sigmas);
 int dkmc_pairwise_pairs_evaluated(dkmc_ctx *ctx, long long *pairs);
 /* share of each SM the overlapped pairwise kernel may occupy: CTAs per SM x threads per CTA */
 int dkmc_ctx_set_pairwise_share(dkmc_ctx *ctx, int blocks_per_sm, int threads_per_block);

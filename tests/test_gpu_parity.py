@@ -495,3 +495,33 @@ def test_potential_overlap_matches_serial(cell_sim, O, torch):
     rows = (dev.N // 2, dev.N // 2 + 2000)
     refc = O.poisson_gridless(dev.site_x, dev.site_y, dev.site_z, dev.lattice, p.pbc, q, p.sigma, p.k, rows=rows)
     assert rel_inf(c1.cpu().numpy()[rows[0]:rows[1]], refc) <= TOL
+
+
+def test_pairwise_cell_list_and_cutoff(cell_sim, O, torch):
+    """cell-list kernel (skips exact zeros) == all-pairs kernel to rounding; the opt-in 10-sigma
+    truncation stays far inside the 1e-10 parity bound (norm-wise) and evaluates far fewer pairs"""
+    from devicekmc_b200._capi import check
+    p, dev, sim, buf, nc = cell_sim
+    lib = dev.ctx.lib
+    args = (dev.ctx.h, dev.pbc, dev.N, buf.lattice.data_ptr(), buf.sigma.data_ptr(), buf.k.data_ptr(),
+            buf.site_x.data_ptr(), buf.site_y.data_ptr(), buf.site_z.data_ptr(), buf.site_charge.data_ptr())
+    out = {}
+    pairs = {}
+    for name, cells, cut in (("all", 0, 0.0), ("cells", 1, 0.0), ("cut10", 1, 10.0)):
+        check(lib.dkmc_ctx_set_pairwise_cells(dev.ctx.h, cells))
+        check(lib.dkmc_ctx_set_pairwise_cutoff(dev.ctx.h, cut))
+        buf.site_potential_charge.fill_(7.0)
+        check(lib.dkmc_poisson_gridless(*args, buf.site_potential_charge.data_ptr()))
+        out[name] = buf.site_potential_charge.clone()
+        pe = C.c_longlong(0)
+        check(lib.dkmc_pairwise_pairs_evaluated(dev.ctx.h, C.byref(pe)))
+        pairs[name] = pe.value
+    check(lib.dkmc_ctx_set_pairwise_cells(dev.ctx.h, 1))
+    check(lib.dkmc_ctx_set_pairwise_cutoff(dev.ctx.h, 0.0))
+    scale = float(out["all"].abs().max())
+    assert scale > 0
+    assert float((out["cells"] - out["all"]).abs().max()) <= 1e-13 * scale
+    big = out["all"].abs() > 1e-6 * scale
+    assert float(((out["cells"] - out["all"]).abs()[big] / out["all"].abs()[big]).max()) <= 1e-12
+    assert float((out["cut10"] - out["all"]).abs().max()) <= 1e-15 * scale
+    assert pairs["cut10"] < pairs["cells"] <= dev.N * int((buf.site_charge != 0).sum().item())
