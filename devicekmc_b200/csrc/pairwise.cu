@@ -365,18 +365,18 @@ __global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
     const double sigma = *sigma_ptr, kc = *k_ptr;
     const double cscale = 1e-10 / (sigma * sqrt(2.0));
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    const int nthr = (int)blockDim.x, targets = 2 * nthr;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_tiles = (row_end - row_begin + targets - 1) / targets;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = (row_end - row_begin + 63) / 64;   // a tile = the 64 targets of one warp
     unsigned long long my_pairs = 0;
 
     while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
-        __syncthreads();
-        const int tile_id = s_tile;
+        // every warp fetches its own tiles: no CTA-wide barrier, a warp with a short cell walk does
+        // not wait for its neighbours
+        int tile_id = 0;
+        if (lane == 0) tile_id = atomicAdd(tile_counter, 1);
+        tile_id = __shfl_sync(0xffffffffu, tile_id, 0);
         if (tile_id >= n_tiles) break;
-        const int ia = row_begin + tile_id * targets + warp * 64 + lane, ib = ia + 32;
+        const int ia = row_begin + tile_id * 64 + lane, ib = ia + 32;
         const bool va = ia < row_end, vb = ib < row_end;
         const int ca = va ? ia : row_end - 1, cb = vb ? ib : row_end - 1;   // idle lanes shadow the last target
         const double xa = x[ca], ya = y[ca], za = z[ca], xb = x[cb], yb = y[cb], zb = z[cb];
@@ -425,13 +425,24 @@ __global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
                 if (va) my_pairs += (unsigned long long)(s1 - s0);
                 if (vb) my_pairs += (unsigned long long)(s1 - s0);
                 int e = s0;
-                for (; e + 1 < s1; e += 2) {
-                    const ChargedSite p0 = src[e], p1 = src[e + 1];
-                    const int j0 = __ldg(src_idx + e), j1 = __ldg(src_idx + e + 1);
+                if (e + 1 < s1) {
+                    // the next two sources are requested before the current two are evaluated
+                    ChargedSite p0 = src[e], p1 = src[e + 1];
+                    int j0 = __ldg(src_idx + e), j1 = __ldg(src_idx + e + 1);
+                    for (; e + 3 < s1; e += 2) {
+                        const ChargedSite n0 = src[e + 2], n1 = src[e + 3];
+                        const int k0 = __ldg(src_idx + e + 2), k1 = __ldg(src_idx + e + 3);
+                        a0 += pair_term(xa, ya, za, ia, p0, j0);
+                        b0 += pair_term(xb, yb, zb, ib, p0, j0);
+                        a1 += pair_term(xa, ya, za, ia, p1, j1);
+                        b1 += pair_term(xb, yb, zb, ib, p1, j1);
+                        p0 = n0; p1 = n1; j0 = k0; j1 = k1;
+                    }
                     a0 += pair_term(xa, ya, za, ia, p0, j0);
                     b0 += pair_term(xb, yb, zb, ib, p0, j0);
                     a1 += pair_term(xa, ya, za, ia, p1, j1);
                     b1 += pair_term(xb, yb, zb, ib, p1, j1);
+                    e += 2;
                 }
                 if (e < s1) {
                     const ChargedSite p0 = src[e];
@@ -542,7 +553,7 @@ static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm
     if (cells) {  // one target per thread
         int grid = ctx->num_sms * blocks_per_sm;
         int *sm_count = nullptr;
-        const int tiles = ceil_div(row_end - row_begin, 2 * threads);
+        const int tiles = ceil_div(ceil_div(row_end - row_begin, 64), threads / 32);
         if (shared_sms) {
             const int fit = (kPwCellFullBlocksPerSm * kPwThreads) / threads;
             grid = ctx->num_sms * (fit > blocks_per_sm ? fit : blocks_per_sm);

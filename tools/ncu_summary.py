@@ -36,7 +36,7 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{rnd}_*.ncu-
         mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         return float(v.replace(",", "")) * mult
     traffic[name] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-    if name == "pairwise_kernel" and "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active" in d:
+    if name == "pairwise_cells_kernel" and "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active" in d:
         fp64_pipe = float(d["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][1].replace(",", ""))
     print(name, kname[:60], "dram bytes/launch", traffic[name])
 lst = os.path.join(ROOT, "gpurun_out", f"launches_{rnd}.csv")
@@ -62,7 +62,7 @@ if os.path.exists(lst):
 # bench.py keys
 tj = os.path.join(ROOT, "profiles", "traffic.json")
 old = json.load(open(tj)) if os.path.exists(tj) else {}
-m = {"spmv": "spmv_tile_kernel", "pairwise": "pairwise_kernel", "rate_table": "rate_rows_kernel"}
+m = {"spmv": "spmv_tile_kernel", "pairwise": "pairwise_cells_kernel", "rate_table": "rate_rows_kernel"}
 old["tiled_1M"] = {k: traffic[v] for k, v in m.items() if v in traffic}
 if fp64_pipe is not None:
     old["pairwise_fp64_pipe_pct"] = fp64_pipe

@@ -29,7 +29,7 @@ pe = C.c_longlong(0); dev.ctx.lib.dkmc_pairwise_pairs_evaluated(dev.ctx.h, C.byr
 nchg = int((buf.site_charge != 0).sum().item())
 print("pairs evaluated %.3e of %.3e (%.1f%%)" % (pe.value, dev.N * nchg, 100.0 * pe.value / (dev.N * nchg)))
 print("serial      total %s ms  cg %.2f pw %.2f iters %d" % (fmt(t), out["solve_ms"], out["pairwise_ms"], out["cg_iterations"]), flush=True)
-for share in ((3, 128), (3, 128), (3, 128)):
+for share in ((2, 128), (2, 160), (2, 192), (3, 96), (4, 96), (5, 64)):
     t, out = run(True, share)
     same_c = bool(torch.equal(ref_c, buf.site_potential_charge))
     err_b = float((ref_b - buf.site_potential_boundary).abs().max() / ref_b.abs().max())
