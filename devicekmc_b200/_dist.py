@@ -3,6 +3,7 @@ dkmc_dist_background_potential.  NCCL communicator bootstrap goes through torch.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -42,7 +43,7 @@ def _device_ints(ptr: int, n: int) -> np.ndarray:
 
 
 class DistributedSolver:
-    def __init__(self, sim: "slab.SlabSim"):
+    def __init__(self, sim: "slab.SlabSim", p2p: bool = True):
         import torch.distributed as dist
         self.sim = sim
         lib = sim.dev.ctx.lib
@@ -56,6 +57,16 @@ class DistributedSolver:
         row_ptr = _device_ints(sp.d_row_ptr, sp.m + 1)
         col = _device_ints(sp.d_col, sp.nnz)
         self.plan = make_plan(row_ptr, col, sim.world, sim.rank, lib.dkmc_spmv_tile_nnz())
+        self.p2p = False
+        if p2p and os.environ.get("DKMC_P2P", "1") != "0":
+            # peer-memory windows: CUDA IPC handles all-gathered through torch.distributed
+            hbuf = C.create_string_buffer(64)
+            check(lib.dkmc_dist_p2p_alloc(sim.dev.ctx.h, sp.m, hbuf))
+            handles = [None] * sim.world
+            dist.all_gather_object(handles, bytes(hbuf.raw))
+            check(lib.dkmc_dist_p2p_open(sim.dev.ctx.h, b"".join(handles)))
+            dist.barrier()
+            self.p2p = True
 
     def solve(self, Vd: float, info: SolveInfo, opts=None):
         s = self.sim

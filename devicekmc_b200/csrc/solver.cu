@@ -985,11 +985,112 @@ static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, co
 // [p.Ap] and [r.D^-1 r, W^T r] — the cluster coarse space is applied from the all-reduced cluster
 // sums, so clusters may straddle slab faces.  K assembly and the cluster detection are replicated
 // (0.4 ms + 0.4 ms at 1 M sites); the solve itself is partitioned.
+// Peer-memory exchange for the per-iteration traffic of the distributed PCG (one process per GPU,
+// windows shared through CUDA IPC, NVLink peer stores).  Every rank owns a window
+//   [ p vector (m doubles) | reduction slots [2][world][kP2pRedCap] | flags [4][world] ]
+// that all ranks map.  An all-reduce is ONE small kernel per rank: push my partial sums into every
+// rank's slot, fence, raise my flag everywhere, wait for everybody's flag here, add the slots in rank
+// order (deterministic, identical on all ranks).  The halo of p is pushed into the neighbours' p
+// vectors the same way.  Slots and flags are double-buffered by the parity of a running operation
+// count; a rank can only start operation n+2 after every rank has raised its flag for n+1, i.e.
+// after everybody finished reading the slots of n.  Latency: one NVLink store + flag round (~3 us)
+// instead of ~20-40 us per NCCL call, of which the PCG needs three per iteration.
+constexpr int kP2pRedCap = 1 << 15;               // doubles per rank and reduction
+constexpr long long kP2pTimeoutCycles = 4000000000ll;  // ~2 s: a lost peer becomes an error, not a hang
+
+struct P2pPeers {
+    unsigned char *base[DKMC_MAX_RANKS];
+    int world, rank;
+    size_t red_off, flag_off;
+};
+
 struct DistState {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // peer-memory windows (dkmc_dist_p2p_alloc / _open)
+    unsigned char *win = nullptr;
+    size_t win_bytes = 0;
+    int m_cap = 0;
+    bool p2p = false;
+    unsigned long long seq = 0;    // reductions (slots and flags 0/1 by parity)
+    unsigned long long hseq = 0;   // halo exchanges (flags 2/3 by parity)
+    P2pPeers peers;
 };
 static DistState *dist_of(dkmc_ctx *ctx) { return static_cast<DistState *>(ctx->dist); }
+
+// flags are written with release and polled with acquire semantics at system scope: ordering comes
+// from the flag accesses themselves, not from (much more expensive) system-wide fences
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long *p2p_flag(const P2pPeers &P, int at_rank, int buf, int of_rank) {
+    return reinterpret_cast<unsigned long long *>(P.base[at_rank] + P.flag_off) + (size_t)buf * P.world + of_rank;
+}
+
+// every rank waits until all ranks have raised flag `buf` to `seq` here; lane r watches rank r
+__device__ __forceinline__ void p2p_wait_all(const P2pPeers &P, int buf, unsigned long long seq, int *err) {
+    for (int r = threadIdx.x; r < P.world; r += blockDim.x) {
+        const unsigned long long *f = p2p_flag(P, P.rank, buf, r);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > kP2pTimeoutCycles) { *err = 1; break; }
+        }
+    }
+}
+
+// dst[0..k) = sum over ranks of src[0..k)   (src may alias dst)
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers P, unsigned long long seq, int k,
+                                                            const double *src, double *dst, int *err) {
+    const int buf = (int)(seq & 1ull);
+    for (int r = 0; r < P.world; ++r) {
+        double *slot = reinterpret_cast<double *>(P.base[r] + P.red_off) + ((size_t)buf * P.world + P.rank) * kP2pRedCap;
+        for (int j = threadIdx.x; j < k; j += blockDim.x) slot[j] = src[j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < P.world; r += blockDim.x) st_release_sys(p2p_flag(P, r, buf, P.rank), seq);
+    p2p_wait_all(P, buf, seq, err);
+    __syncthreads();
+    const volatile double *mine = reinterpret_cast<const volatile double *>(P.base[P.rank] + P.red_off) +
+                                  (size_t)buf * P.world * kP2pRedCap;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < P.world; ++r) acc += mine[(size_t)r * kP2pRedCap + j];
+        dst[j] = acc;
+    }
+}
+
+struct P2pHalo {
+    int n_send, n_recv;
+    int send_peer[DKMC_MAX_HALO_SEGMENTS], send_begin[DKMC_MAX_HALO_SEGMENTS], send_end[DKMC_MAX_HALO_SEGMENTS];
+    int recv_peer[DKMC_MAX_HALO_SEGMENTS];
+};
+
+// pushes my boundary rows of p (it lives at offset 0 of the window) into the neighbours' p vectors,
+// then waits for theirs.  One CTA: the halo of an x-slab is a few hundred KB.
+__global__ void __launch_bounds__(1024) p2p_halo_kernel(P2pPeers P, P2pHalo H, unsigned long long seq, int *err) {
+    const int buf = 2 + (int)(seq & 1ull);
+    const double *mine = reinterpret_cast<const double *>(P.base[P.rank]);
+    for (int sgm = 0; sgm < H.n_send; ++sgm) {
+        double *theirs = reinterpret_cast<double *>(P.base[H.send_peer[sgm]]);
+        for (int i = H.send_begin[sgm] + threadIdx.x; i < H.send_end[sgm]; i += blockDim.x) theirs[i] = mine[i];
+    }
+    __syncthreads();
+    for (int sgm = threadIdx.x; sgm < H.n_send; sgm += blockDim.x) st_release_sys(p2p_flag(P, H.send_peer[sgm], buf, P.rank), seq);
+    for (int sgm = threadIdx.x; sgm < H.n_recv; sgm += blockDim.x) {
+        const unsigned long long *f = p2p_flag(P, P.rank, buf, H.recv_peer[sgm]);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > kP2pTimeoutCycles) { *err = 1; break; }
+        }
+    }
+    __syncthreads();
+}
 
 #define DKMC_NCCL(call)                                                                       \
     do {                                                                                      \
@@ -1129,6 +1230,138 @@ __global__ void __launch_bounds__(kVecThreads) dist_inf_norms_kernel(int ra, int
     }
 }
 
+// ---------------------------------------------------------------- fused compute + exchange kernels (peer memory)
+// With open peer windows an iteration of the distributed PCG is four kernels and no collective call:
+//   SpMV (+ local p.Ap)  ->  update (prologue: all-reduce of p.Ap over peer memory)
+//   ->  reduce_scalars (cluster partial sums, all-reduce of [r.D^-1 r, cluster sums], beta, convergence)
+//   ->  direction (epilogue of the last CTA: push the halo rows of p to the neighbours, wait for theirs)
+__device__ __forceinline__ double *p2p_slot(const P2pPeers &P, int at_rank, int buf, int of_rank) {
+    return reinterpret_cast<double *>(P.base[at_rank] + P.red_off) + ((size_t)buf * P.world + of_rank) * kP2pRedCap;
+}
+
+__global__ void __launch_bounds__(kVecThreads) dist_update_p2p_kernel(P2pPeers P, unsigned long long rseq, int ra, int rb,
+                                                                     double *x, double *r, const double *__restrict__ p,
+                                                                     const double *__restrict__ Ap,
+                                                                     const double *__restrict__ dinv,
+                                                                     const double *pAp_local, double *partials,
+                                                                     CgScalars *sc, double *out) {
+    __shared__ double red[32];
+    __shared__ double s_pAp;
+    if (sc->done) return;
+    const int buf = (int)(rseq & 1ull);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // this rank's p.Ap goes to everybody
+        const double v = *pAp_local;
+        for (int q = 0; q < P.world; ++q) p2p_slot(P, q, buf, P.rank)[0] = v;
+        for (int q = 0; q < P.world; ++q) st_release_sys(p2p_flag(P, q, buf, P.rank), rseq);
+    }
+    p2p_wait_all(P, buf, rseq, &sc->pad);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int q = 0; q < P.world; ++q) acc += *(const volatile double *)p2p_slot(P, P.rank, buf, q);
+        s_pAp = acc;
+    }
+    __syncthreads();
+    const double alpha = sc->rz / s_pAp;
+    double local = 0.0;
+    for (int i = ra + blockIdx.x * blockDim.x + threadIdx.x; i < rb; i += gridDim.x * blockDim.x) {
+        x[i] += alpha * p[i];
+        double ri = r[i] - alpha * Ap[i];
+        r[i] = ri;
+        local += ri * ri * dinv[i];
+    }
+    double tot = block_sum(local, red);
+    grid_sum_finish(tot, partials, &sc->cnt_b, out, red);
+}
+
+// one CTA: cluster partial sums of r over own rows, all-reduce of red[1 .. 4+n), then beta / convergence
+__global__ void __launch_bounds__(256) dist_reduce_scalars_kernel(P2pPeers P, unsigned long long rseq, int n_cl, int ra,
+                                                                   int rb, const int *__restrict__ seg_start,
+                                                                   const int *__restrict__ seg_len,
+                                                                   const int *__restrict__ mem_row, const double *r,
+                                                                   const double *__restrict__ w, double *red,
+                                                                   CgScalars *sc) {
+    __shared__ double sh[32];
+    if (sc->done) return;
+    const int buf = (int)(rseq & 1ull);
+    const int k = 3 + n_cl;
+    for (int s = threadIdx.x; s < n_cl; s += blockDim.x) {
+        double sum = 0.0;
+        if (seg_start[s] == s) {
+            const int len = seg_len[s];
+            for (int q = 0; q < len; ++q) {
+                const int row = mem_row[s + q];
+                if (row >= ra && row < rb) sum += r[row];
+            }
+        }
+        red[4 + s] = sum;
+    }
+    __syncthreads();
+    for (int q = 0; q < P.world; ++q) {
+        double *slot = p2p_slot(P, q, buf, P.rank);
+        for (int j = threadIdx.x; j < k; j += blockDim.x) slot[j] = red[1 + j];
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < P.world; q += blockDim.x) st_release_sys(p2p_flag(P, q, buf, P.rank), rseq);
+    p2p_wait_all(P, buf, rseq, &sc->pad);
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        double acc = 0.0;
+        for (int q = 0; q < P.world; ++q) acc += ((const volatile double *)p2p_slot(P, P.rank, buf, q))[j];
+        red[1 + j] = acc;
+    }
+    __syncthreads();
+    double c1 = coarse_dot(n_cl, seg_start, w, red + 4, red + 4, sh);
+    if (threadIdx.x == 0) {
+        double rzn = red[1] + c1;
+        sc->beta = rzn / sc->rz;
+        sc->rz = rzn;
+        sc->iters += 1;
+        if (rzn <= sc->stop || sc->iters >= sc->max_iter || !(rzn == rzn)) sc->done = 1;
+    }
+}
+
+// p = D^-1 r + W E^-1 s + beta p over own rows; the last CTA to finish pushes this rank's boundary
+// rows into the neighbours' p vectors and waits for theirs, so the next SpMV finds its halo in place
+__global__ void __launch_bounds__(kVecThreads) dist_direction_p2p_kernel(int ra, int rb, const double *__restrict__ r,
+                                                                        Precond Pc, const double *__restrict__ csum,
+                                                                        double *__restrict__ p, CgScalars *sc, int first,
+                                                                        P2pPeers P, P2pHalo H, unsigned long long hseq) {
+    __shared__ bool is_last;
+    if (!first && sc->done) return;
+    const double beta = first ? 0.0 : sc->beta;
+    for (int i = ra + blockIdx.x * blockDim.x + threadIdx.x; i < rb; i += gridDim.x * blockDim.x) {
+        double z = r[i] * Pc.dinv[i];
+        const int s = Pc.pos ? Pc.pos[i] : -1;
+        if (s >= 0) { const int st = Pc.seg_start[s]; z += Pc.w[st] * csum[st]; }
+        p[i] = first ? z : z + beta * p[i];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&sc->cnt_d, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int buf = 2 + (int)(hseq & 1ull);
+    const double *mine = reinterpret_cast<const double *>(P.base[P.rank]);
+    for (int sgm = 0; sgm < H.n_send; ++sgm) {
+        double *theirs = reinterpret_cast<double *>(P.base[H.send_peer[sgm]]);
+        for (int i = H.send_begin[sgm] + threadIdx.x; i < H.send_end[sgm]; i += blockDim.x)
+            theirs[i] = __ldcg(mine + i);
+    }
+    __syncthreads();
+    for (int sgm = threadIdx.x; sgm < H.n_send; sgm += blockDim.x) st_release_sys(p2p_flag(P, H.send_peer[sgm], buf, P.rank), hseq);
+    for (int sgm = threadIdx.x; sgm < H.n_recv; sgm += blockDim.x) {
+        const unsigned long long *f = p2p_flag(P, P.rank, buf, H.recv_peer[sgm]);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < hseq) {
+            if (clock64() - t0 > kP2pTimeoutCycles) { sc->pad = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sc->cnt_d = 0u;
+}
+
 struct DistWork {
     CgWork w;
     const dkmc_dist_plan *plan;
@@ -1147,6 +1380,33 @@ static int halo_exchange(dkmc_ctx *ctx, const DistWork &d, double *v) {
     for (int k = 0; k < pl->n_recv; ++k)
         DKMC_NCCL(ncclRecv(v + pl->recv_begin[k], (size_t)(pl->recv_end[k] - pl->recv_begin[k]), ncclDouble, pl->recv_peer[k], ds->comm, ctx->stream));
     DKMC_NCCL(ncclGroupEnd());
+    return DKMC_OK;
+}
+
+// sum of k doubles over the ranks, in place: peer memory when the windows are open, else NCCL
+static int dist_allreduce(dkmc_ctx *ctx, double *buf, size_t k, CgScalars *sc) {
+    DistState *ds = dist_of(ctx);
+    if (ds->p2p && k <= (size_t)kP2pRedCap) {
+        ++ds->seq;
+        DKMC_LAUNCH(ctx, p2p_allreduce_kernel, 1, 256, 0, ds->peers, ds->seq, (int)k, buf, buf, &sc->pad);
+        return DKMC_OK;
+    }
+    DKMC_NCCL(ncclAllReduce(buf, buf, k, ncclDouble, ncclSum, ds->comm, ctx->stream));
+    return DKMC_OK;
+}
+
+// halo of the search direction p: pushed into the neighbours' windows when p lives in the window
+static int dist_halo_p(dkmc_ctx *ctx, const DistWork &d, double *p, CgScalars *sc) {
+    DistState *ds = dist_of(ctx);
+    if (!(ds->p2p && p == reinterpret_cast<double *>(ds->win))) return halo_exchange(ctx, d, p);
+    const dkmc_dist_plan *pl = d.plan;
+    if (pl->n_send == 0 && pl->n_recv == 0) return DKMC_OK;
+    P2pHalo H;
+    H.n_send = pl->n_send; H.n_recv = pl->n_recv;
+    for (int k = 0; k < pl->n_send; ++k) { H.send_peer[k] = pl->send_peer[k]; H.send_begin[k] = pl->send_begin[k]; H.send_end[k] = pl->send_end[k]; }
+    for (int k = 0; k < pl->n_recv; ++k) H.recv_peer[k] = pl->recv_peer[k];
+    ++ds->hseq;
+    DKMC_LAUNCH(ctx, p2p_halo_kernel, 1, 1024, 0, ds->peers, H, ds->hseq, &sc->pad);
     return DKMC_OK;
 }
 
@@ -1173,33 +1433,85 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
         DKMC_LAUNCH(ctx, cluster_partial_kernel, ceil_div(n, 128), 128, 0, n, d.ra, d.rb, d.seg_start, d.seg_len, d.mem_row, r, d.red + 4);
         DKMC_LAUNCH(ctx, cluster_partial_kernel, ceil_div(n, 128), 128, 0, n, d.ra, d.rb, d.seg_start, d.seg_len, d.mem_row, d_b, d.red + 4 + n);
     }
-    DKMC_NCCL(ncclAllReduce(d.red + 1, d.red + 1, (size_t)3 + 2 * (size_t)n, ncclDouble, ncclSum, ds->comm, ctx->stream));
+    if ((rc = dist_allreduce(ctx, d.red + 1, (size_t)3 + 2 * (size_t)n, w.sc))) return rc;
     DKMC_LAUNCH(ctx, dist_scalars_init_kernel, 1, 256, 0, n, d.seg_start, w.P.w, d.red, tol, max_iter, w.sc);
-    DKMC_LAUNCH(ctx, dist_direction_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.P, d.red + 4, w.p, w.sc, 1);
+    // fused compute + exchange kernels when the windows are open, p lives in this rank's window and the
+    // cluster sums fit a reduction slot
+    const bool fused = ds->p2p && w.p == reinterpret_cast<double *>(ds->win) && (size_t)3 + 2 * (size_t)n <= (size_t)kP2pRedCap &&
+                       !(g_flags & 128);
+    P2pHalo H;
+    memset(&H, 0, sizeof(H));
+    if (fused) {
+        const dkmc_dist_plan *pl = d.plan;
+        H.n_send = pl->n_send; H.n_recv = pl->n_recv;
+        for (int k = 0; k < pl->n_send; ++k) { H.send_peer[k] = pl->send_peer[k]; H.send_begin[k] = pl->send_begin[k]; H.send_end[k] = pl->send_end[k]; }
+        for (int k = 0; k < pl->n_recv; ++k) H.recv_peer[k] = pl->recv_peer[k];
+        DKMC_LAUNCH(ctx, dist_direction_p2p_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.P, d.red + 4, w.p, w.sc, 1, ds->peers, H,
+                    ++ds->hseq);
+    } else {
+        DKMC_LAUNCH(ctx, dist_direction_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.P, d.red + 4, w.p, w.sc, 1);
+    }
     CgScalars h;
     memset(&h, 0, sizeof(h));
     int launched = 0;
     if (check_every < 1) check_every = 1;
     while (true) {
-        for (int k = 0; k < check_every; ++k) {
-            if ((rc = halo_exchange(ctx, d, w.p))) return rc;
+        static const bool prof = getenv("DKMC_DIST_PROF") != nullptr;
+        static int prof_batches = 0;
+        cudaEvent_t pe[33][5];
+        const bool do_prof = prof && fused && prof_batches < 3 && check_every <= 32;
+        if (do_prof) for (int a = 0; a < 33; ++a) for (int b = 0; b < 5; ++b) cudaEventCreate(&pe[a][b]);
+        for (int k = 0; k < check_every && fused; ++k) {
+            if (do_prof) cudaEventRecord(pe[k][0], ctx->stream);
             if (nt > 0) {
                 if ((rc = launch_spmv<1>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap, w.tile_row + d.t0, w.p, nullptr,
                                          w.partials, &w.sc->cnt_c, d.red + 0, &w.sc->done, m + 32))) return rc;
             } else
                 DKMC_CUDA(cudaMemsetAsync(d.red, 0, sizeof(double), ctx->stream));
-            DKMC_NCCL(ncclAllReduce(d.red, d.red, 1, ncclDouble, ncclSum, ds->comm, ctx->stream));
+            if (do_prof) cudaEventRecord(pe[k][1], ctx->stream);
+            DKMC_LAUNCH(ctx, dist_update_p2p_kernel, vg, kVecThreads, 0, ds->peers, ++ds->seq, d.ra, d.rb, d_x, r, w.p, w.Ap,
+                        w.dinv, d.red + 0, w.partials, w.sc, d.red + 1);
+            if (do_prof) cudaEventRecord(pe[k][2], ctx->stream);
+            DKMC_LAUNCH(ctx, dist_reduce_scalars_kernel, 1, 256, 0, ds->peers, ++ds->seq, n, d.ra, d.rb, d.seg_start, d.seg_len,
+                        d.mem_row, r, w.P.w, d.red, w.sc);
+            if (do_prof) cudaEventRecord(pe[k][3], ctx->stream);
+            DKMC_LAUNCH(ctx, dist_direction_p2p_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.P, d.red + 4, w.p, w.sc, 0, ds->peers,
+                        H, ++ds->hseq);
+            if (do_prof) cudaEventRecord(pe[k][4], ctx->stream);
+        }
+        if (do_prof) {
+            cudaStreamSynchronize(ctx->stream);
+            double acc[4] = {0, 0, 0, 0};
+            for (int k = 0; k < check_every; ++k)
+                for (int b = 0; b < 4; ++b) { float ms = 0; cudaEventElapsedTime(&ms, pe[k][b], pe[k][b + 1]); acc[b] += ms; }
+            fprintf(stderr, "rank %d n_cl %d: us per iteration: spmv %.1f update %.1f reduce_scalars %.1f direction+halo %.1f\n", ds->rank, n,
+                    1e3 * acc[0] / check_every, 1e3 * acc[1] / check_every, 1e3 * acc[2] / check_every, 1e3 * acc[3] / check_every);
+            for (int a = 0; a < 33; ++a) for (int b = 0; b < 5; ++b) cudaEventDestroy(pe[a][b]);
+            ++prof_batches;
+        }
+        for (int k = 0; k < check_every && !fused; ++k) {
+            if ((rc = dist_halo_p(ctx, d, w.p, w.sc))) return rc;
+            if (nt > 0) {
+                if ((rc = launch_spmv<1>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap, w.tile_row + d.t0, w.p, nullptr,
+                                         w.partials, &w.sc->cnt_c, d.red + 0, &w.sc->done, m + 32))) return rc;
+            } else
+                DKMC_CUDA(cudaMemsetAsync(d.red, 0, sizeof(double), ctx->stream));
+            if ((rc = dist_allreduce(ctx, d.red, 1, w.sc))) return rc;
             DKMC_LAUNCH(ctx, dist_update_kernel, vg, kVecThreads, 0, d.ra, d.rb, d_x, r, w.p, w.Ap, w.dinv, d.red + 0,
                         w.partials, w.sc, d.red + 1);
             if (n > 0)
                 DKMC_LAUNCH(ctx, cluster_partial_kernel, ceil_div(n, 128), 128, 0, n, d.ra, d.rb, d.seg_start, d.seg_len, d.mem_row, r, d.red + 4);
-            DKMC_NCCL(ncclAllReduce(d.red + 1, d.red + 1, (size_t)3 + (size_t)n, ncclDouble, ncclSum, ds->comm, ctx->stream));
+            if ((rc = dist_allreduce(ctx, d.red + 1, (size_t)3 + (size_t)n, w.sc))) return rc;
             DKMC_LAUNCH(ctx, dist_scalars_kernel, 1, 256, 0, n, d.seg_start, w.P.w, d.red, w.sc);
             DKMC_LAUNCH(ctx, dist_direction_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.P, d.red + 4, w.p, w.sc, 0);
         }
         launched += check_every;
         DKMC_CUDA(cudaMemcpyAsync(&h, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
         DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h.pad != 0) {
+            set_error("distributed PCG: a peer did not answer within the time limit (peer-memory exchange)");
+            return DKMC_ERR_CUDA;
+        }
         if (h.done || launched >= max_iter) break;
     }
     *iters_out = h.iters;
@@ -1457,11 +1769,57 @@ int dkmc_dist_init(dkmc_ctx *ctx, int rank, int world, const char *id128) {
     return DKMC_OK;
 }
 
+int dkmc_dist_p2p_alloc(dkmc_ctx *ctx, int m, char *ipc_handle64) {
+    DKMC_REQUIRE(ctx && ipc_handle64 && m > 0, "arguments");
+    DistState *ds = dist_of(ctx);
+    DKMC_REQUIRE(ds != nullptr, "dkmc_dist_init must be called first");
+    DKMC_REQUIRE(ds->win == nullptr, "window already allocated");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "cudaIpcMemHandle_t larger than 64 bytes");
+    const size_t pbytes = (((size_t)m + 64) * sizeof(double) + 255) & ~(size_t)255;
+    const size_t rbytes = (size_t)2 * ds->world * kP2pRedCap * sizeof(double);
+    const size_t fbytes = (size_t)4 * DKMC_MAX_RANKS * sizeof(unsigned long long);
+    ds->peers.red_off = pbytes;
+    ds->peers.flag_off = pbytes + rbytes;
+    ds->win_bytes = pbytes + rbytes + fbytes;
+    DKMC_CUDA(cudaMalloc(&ds->win, ds->win_bytes));
+    DKMC_CUDA(cudaMemset(ds->win, 0, ds->win_bytes));
+    ds->m_cap = m;
+    cudaIpcMemHandle_t h;
+    DKMC_CUDA(cudaIpcGetMemHandle(&h, ds->win));
+    memset(ipc_handle64, 0, 64);
+    memcpy(ipc_handle64, &h, sizeof(h));
+    return DKMC_OK;
+}
+
+int dkmc_dist_p2p_open(dkmc_ctx *ctx, const char *ipc_handles64) {
+    DKMC_REQUIRE(ctx && ipc_handles64, "arguments");
+    DistState *ds = dist_of(ctx);
+    DKMC_REQUIRE(ds != nullptr && ds->win != nullptr, "dkmc_dist_p2p_alloc must be called first");
+    ds->peers.world = ds->world;
+    ds->peers.rank = ds->rank;
+    for (int r = 0; r < ds->world; ++r) {
+        if (r == ds->rank) { ds->peers.base[r] = ds->win; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handles64 + (size_t)r * 64, sizeof(h));
+        void *ptr = nullptr;
+        DKMC_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ds->peers.base[r] = static_cast<unsigned char *>(ptr);
+    }
+    ds->seq = 0;
+    ds->hseq = 0;
+    ds->p2p = true;
+    return DKMC_OK;
+}
+
 int dkmc_dist_finalize(dkmc_ctx *ctx) {
     DKMC_REQUIRE(ctx != nullptr, "ctx");
     DistState *ds = dist_of(ctx);
     if (ds) {
         cudaStreamSynchronize(ctx->stream);
+        if (ds->p2p)
+            for (int r = 0; r < ds->world; ++r)
+                if (r != ds->rank && ds->peers.base[r]) cudaIpcCloseMemHandle(ds->peers.base[r]);
+        if (ds->win) cudaFree(ds->win);
         if (ds->comm) ncclCommDestroy(ds->comm);
         delete ds;
         ctx->dist = nullptr;
@@ -1518,6 +1876,9 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
         if (d.rb <= d.ra) d.t1 = d.t0;
     }
     if ((rc = ensure<double>(ctx, S_DIST_RED, (size_t)4 + 2 * (size_t)d.n_cl + 8, &d.red))) return rc;
+    // with open peer windows the search direction lives in this rank's window (offset 0), where the
+    // neighbours push their boundary rows
+    if (ds->p2p && m <= ds->m_cap) d.w.p = reinterpret_cast<double *>(ds->win);
     double *x = d_site_potential_boundary + NL;
     rc = dist_solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, d, o, info, m + NR);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;

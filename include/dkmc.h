@@ -260,6 +260,13 @@ int dkmc_spmv_tile_nnz(void); /* rows are assigned to SpMV tiles by row start, t
 int dkmc_dist_unique_id(char *id128);
 int dkmc_dist_init(dkmc_ctx *ctx, int rank, int world, const char *id128);
 int dkmc_dist_finalize(dkmc_ctx *ctx);
+/* Optional: peer-memory windows for the per-iteration exchange of the distributed PCG (halo of the
+ * search direction and the two all-reduces) — NVLink peer stores and flags inside small kernels
+ * instead of three NCCL calls per iteration.  Every rank calls _alloc (m = interior rows; returns a
+ * 64-byte CUDA IPC handle), the host all-gathers the handles in rank order, every rank calls _open
+ * with the world * 64 bytes.  Without it dkmc_dist_background_potential uses NCCL throughout. */
+int dkmc_dist_p2p_alloc(dkmc_ctx *ctx, int m, char *ipc_handle64);
+int dkmc_dist_p2p_open(dkmc_ctx *ctx, const char *ipc_handles64);
 /* background_potential_gpu_sparse (gpu_solvers.h:139-141) over `world` GPUs; on return every rank
  * holds the full d_site_potential_boundary. */
 int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd,
