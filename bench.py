@@ -374,11 +374,10 @@ def main():
     ap.add_argument("--events-per-step", type=int, default=850,
                     help="--impl reference: events per KMC step the bounded event-loop sample is scaled to "
                          "(what the GPU arm executes per step on tiled_1M after warm-up)")
-    ap.add_argument("--distributed-cg", action="store_true",
-                    help="N>1: slab-partition the CG over the ranks (halo + 2 all-reduces per iteration over NCCL). Default: "
-                         "every rank runs the whole CG beside its share of the pairwise sum — faster at 1 M sites, where "
-                         "three NCCL collectives cost more than one rank's share of an iteration")
-    ap.add_argument("--replicated-cg", action="store_true", help=argparse.SUPPRESS)  # former spelling of the default
+    ap.add_argument("--replicated-cg", action="store_true",
+                    help="N>1: every rank runs the whole CG beside its share of the pairwise sum, instead of the default "
+                         "slab-partitioned CG whose per-iteration exchange goes through NVLink peer memory")
+    ap.add_argument("--distributed-cg", action="store_true", help=argparse.SUPPRESS)  # the default since round 1
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

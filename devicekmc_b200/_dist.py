@@ -61,12 +61,16 @@ class DistributedSolver:
         if p2p and os.environ.get("DKMC_P2P", "1") != "0":
             # peer-memory windows: CUDA IPC handles all-gathered through torch.distributed
             hbuf = C.create_string_buffer(64)
-            check(lib.dkmc_dist_p2p_alloc(sim.dev.ctx.h, sp.m, hbuf))
+            ok = lib.dkmc_dist_p2p_alloc(sim.dev.ctx.h, sp.m, hbuf) == 0
             handles = [None] * sim.world
-            dist.all_gather_object(handles, bytes(hbuf.raw))
-            check(lib.dkmc_dist_p2p_open(sim.dev.ctx.h, b"".join(handles)))
-            dist.barrier()
-            self.p2p = True
+            dist.all_gather_object(handles, bytes(hbuf.raw) if ok else b"")
+            if all(len(h) == 64 for h in handles):
+                ok = lib.dkmc_dist_p2p_open(sim.dev.ctx.h, b"".join(handles)) == 0
+            else:
+                ok = False
+            flags = [None] * sim.world
+            dist.all_gather_object(flags, bool(ok))
+            self.p2p = all(flags)   # every rank must have mapped every window
 
     def solve(self, Vd: float, info: SolveInfo, opts=None):
         s = self.sim

@@ -1044,9 +1044,15 @@ __device__ __forceinline__ void p2p_wait_all(const P2pPeers &P, int buf, unsigne
     }
 }
 
-// dst[0..k) = sum over ranks of src[0..k)   (src may alias dst)
+struct P2pHalo {
+    int n_send, n_recv;
+    int send_peer[DKMC_MAX_HALO_SEGMENTS], send_begin[DKMC_MAX_HALO_SEGMENTS], send_end[DKMC_MAX_HALO_SEGMENTS];
+    int recv_peer[DKMC_MAX_HALO_SEGMENTS];
+};
+
+// dst[0..k) = sum (or max) over ranks of src[0..k)   (src may alias dst)
 __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers P, unsigned long long seq, int k,
-                                                            const double *src, double *dst, int *err) {
+                                                            const double *src, double *dst, int *err, int op_max) {
     const int buf = (int)(seq & 1ull);
     for (int r = 0; r < P.world; ++r) {
         double *slot = reinterpret_cast<double *>(P.base[r] + P.red_off) + ((size_t)buf * P.world + P.rank) * kP2pRedCap;
@@ -1059,17 +1065,62 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers P, unsigned
     const volatile double *mine = reinterpret_cast<const volatile double *>(P.base[P.rank] + P.red_off) +
                                   (size_t)buf * P.world * kP2pRedCap;
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        double acc = 0.0;
-        for (int r = 0; r < P.world; ++r) acc += mine[(size_t)r * kP2pRedCap + j];
+        double acc = mine[j];
+        for (int r = 1; r < P.world; ++r) {
+            const double v = mine[(size_t)r * kP2pRedCap + j];
+            acc = op_max ? fmax(acc, v) : acc + v;
+        }
         dst[j] = acc;
     }
 }
 
-struct P2pHalo {
-    int n_send, n_recv;
-    int send_peer[DKMC_MAX_HALO_SEGMENTS], send_begin[DKMC_MAX_HALO_SEGMENTS], send_end[DKMC_MAX_HALO_SEGMENTS];
-    int recv_peer[DKMC_MAX_HALO_SEGMENTS];
-};
+// window[i] = src[i] over own rows, boundary rows also into the neighbours' windows; the last CTA
+// raises the flags and waits for the neighbours' rows (same protocol as dist_direction_p2p_kernel)
+__global__ void __launch_bounds__(256) p2p_scatter_rows_kernel(int ra, int rb, const double *__restrict__ src, P2pPeers P,
+                                                               P2pHalo H, unsigned long long hseq, unsigned int *counter,
+                                                               int *err) {
+    __shared__ bool is_last;
+    double *mine = reinterpret_cast<double *>(P.base[P.rank]);
+    bool pushed = false;
+    for (int i = ra + blockIdx.x * blockDim.x + threadIdx.x; i < rb; i += gridDim.x * blockDim.x) {
+        const double v = src[i];
+        mine[i] = v;
+        for (int sgm = 0; sgm < H.n_send; ++sgm)
+            if (i >= H.send_begin[sgm] && i < H.send_end[sgm]) {
+                reinterpret_cast<double *>(P.base[H.send_peer[sgm]])[i] = v;
+                pushed = true;
+            }
+    }
+    if (__syncthreads_or(pushed)) __threadfence_system();
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int buf = 2 + (int)(hseq & 1ull);
+    for (int sgm = threadIdx.x; sgm < H.n_send; sgm += blockDim.x) st_release_sys(p2p_flag(P, H.send_peer[sgm], buf, P.rank), hseq);
+    for (int sgm = threadIdx.x; sgm < H.n_recv; sgm += blockDim.x) {
+        const unsigned long long *f = p2p_flag(P, P.rank, buf, H.recv_peer[sgm]);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < hseq) {
+            if (clock64() - t0 > kP2pTimeoutCycles) { *err = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
+// x[i] = window_of_owner(i)[i] for the rows of the other ranks (peer reads over NVLink)
+struct P2pRows { int world; int begin[DKMC_MAX_RANKS], end[DKMC_MAX_RANKS]; };
+__global__ void __launch_bounds__(256) p2p_pull_rows_kernel(P2pPeers P, P2pRows R, double *__restrict__ x) {
+    for (int q = 0; q < R.world; ++q) {
+        if (q == P.rank) continue;
+        const double *theirs = reinterpret_cast<const double *>(P.base[q]);
+        for (int i = R.begin[q] + blockIdx.x * blockDim.x + threadIdx.x; i < R.end[q]; i += gridDim.x * blockDim.x)
+            x[i] = __ldcv(theirs + i);
+    }
+}
 
 // pushes my boundary rows of p (it lives at offset 0 of the window) into the neighbours' p vectors,
 // then waits for theirs.  One CTA: the halo of an x-slab is a few hundred KB.
@@ -1330,12 +1381,21 @@ __global__ void __launch_bounds__(kVecThreads) dist_direction_p2p_kernel(int ra,
     __shared__ bool is_last;
     if (!first && sc->done) return;
     const double beta = first ? 0.0 : sc->beta;
+    bool pushed = false;
     for (int i = ra + blockIdx.x * blockDim.x + threadIdx.x; i < rb; i += gridDim.x * blockDim.x) {
         double z = r[i] * Pc.dinv[i];
         const int s = Pc.pos ? Pc.pos[i] : -1;
         if (s >= 0) { const int st = Pc.seg_start[s]; z += Pc.w[st] * csum[st]; }
-        p[i] = first ? z : z + beta * p[i];
+        const double pv = first ? z : z + beta * p[i];
+        p[i] = pv;
+        // boundary rows go straight into the neighbours' p vectors (every CTA pushes what it computes)
+        for (int sgm = 0; sgm < H.n_send; ++sgm)
+            if (i >= H.send_begin[sgm] && i < H.send_end[sgm]) {
+                reinterpret_cast<double *>(P.base[H.send_peer[sgm]])[i] = pv;
+                pushed = true;
+            }
     }
+    if (__syncthreads_or(pushed)) __threadfence_system();   // peer stores of this CTA before its arrival below
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&sc->cnt_d, 1u) == gridDim.x - 1);
@@ -1343,12 +1403,6 @@ __global__ void __launch_bounds__(kVecThreads) dist_direction_p2p_kernel(int ra,
     if (!is_last) return;
     __threadfence();
     const int buf = 2 + (int)(hseq & 1ull);
-    const double *mine = reinterpret_cast<const double *>(P.base[P.rank]);
-    for (int sgm = 0; sgm < H.n_send; ++sgm) {
-        double *theirs = reinterpret_cast<double *>(P.base[H.send_peer[sgm]]);
-        for (int i = H.send_begin[sgm] + threadIdx.x; i < H.send_end[sgm]; i += blockDim.x)
-            theirs[i] = __ldcg(mine + i);
-    }
     __syncthreads();
     for (int sgm = threadIdx.x; sgm < H.n_send; sgm += blockDim.x) st_release_sys(p2p_flag(P, H.send_peer[sgm], buf, P.rank), hseq);
     for (int sgm = threadIdx.x; sgm < H.n_recv; sgm += blockDim.x) {
@@ -1384,14 +1438,14 @@ static int halo_exchange(dkmc_ctx *ctx, const DistWork &d, double *v) {
 }
 
 // sum of k doubles over the ranks, in place: peer memory when the windows are open, else NCCL
-static int dist_allreduce(dkmc_ctx *ctx, double *buf, size_t k, CgScalars *sc) {
+static int dist_allreduce(dkmc_ctx *ctx, double *buf, size_t k, CgScalars *sc, bool op_max = false) {
     DistState *ds = dist_of(ctx);
     if (ds->p2p && k <= (size_t)kP2pRedCap) {
         ++ds->seq;
-        DKMC_LAUNCH(ctx, p2p_allreduce_kernel, 1, 256, 0, ds->peers, ds->seq, (int)k, buf, buf, &sc->pad);
+        DKMC_LAUNCH(ctx, p2p_allreduce_kernel, 1, 256, 0, ds->peers, ds->seq, (int)k, buf, buf, &sc->pad, op_max ? 1 : 0);
         return DKMC_OK;
     }
-    DKMC_NCCL(ncclAllReduce(buf, buf, k, ncclDouble, ncclSum, ds->comm, ctx->stream));
+    DKMC_NCCL(ncclAllReduce(buf, buf, k, ncclDouble, op_max ? ncclMax : ncclSum, ds->comm, ctx->stream));
     return DKMC_OK;
 }
 
@@ -1410,6 +1464,37 @@ static int dist_halo_p(dkmc_ctx *ctx, const DistWork &d, double *p, CgScalars *s
     return DKMC_OK;
 }
 
+static void fill_halo_desc(const dkmc_dist_plan *pl, P2pHalo *H) {
+    memset(H, 0, sizeof(*H));
+    H->n_send = pl->n_send; H->n_recv = pl->n_recv;
+    for (int k = 0; k < pl->n_send; ++k) { H->send_peer[k] = pl->send_peer[k]; H->send_begin[k] = pl->send_begin[k]; H->send_end[k] = pl->send_end[k]; }
+    for (int k = 0; k < pl->n_recv; ++k) H->recv_peer[k] = pl->recv_peer[k];
+}
+
+// Makes v's own rows and halo available to this rank's SpMV.  Peer memory: the rows are copied into
+// the window (which the search direction does not occupy at that moment) and the boundary rows
+// pushed to the neighbours; *use = the window.  Otherwise NCCL send/recv in place; *use = v.
+static int dist_halo_any(dkmc_ctx *ctx, const DistWork &d, double *v, CgScalars *sc, const double **use, int *readable,
+                         int v_readable) {
+    DistState *ds = dist_of(ctx);
+    const int m_rows = d.plan->row_end[ds->world - 1];
+    if (ds->p2p && m_rows <= ds->m_cap && !(g_flags & 128)) {
+        P2pHalo H;
+        fill_halo_desc(d.plan, &H);
+        const int rows = d.rb - d.ra;
+        int grid = ceil_div(rows > 0 ? rows : 1, 256);
+        if (grid > ctx->num_sms * 4) grid = ctx->num_sms * 4;
+        DKMC_LAUNCH(ctx, p2p_scatter_rows_kernel, grid, 256, 0, d.ra, d.rb, v, ds->peers, H, ++ds->hseq, &sc->cnt_d, &sc->pad);
+        *use = reinterpret_cast<const double *>(ds->win);
+        *readable = ds->m_cap + 32;
+        return DKMC_OK;
+    }
+    int rc = halo_exchange(ctx, d, v);
+    *use = v;
+    *readable = v_readable;
+    return rc;
+}
+
 static int dist_grid(const dkmc_ctx *ctx, int n) {
     int g = ceil_div(n > 0 ? n : 1, kVecThreads);
     int cap = ctx->num_sms * 8;
@@ -1424,9 +1509,11 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
     const int nt = d.t1 - d.t0, rows = d.rb - d.ra, vg = dist_grid(ctx, rows), n = d.n_cl;
     double *r = w.r[0];
     int rc;
-    if ((rc = halo_exchange(ctx, d, d_x))) return rc;
-    if ((rc = launch_spmv<2>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, d_x, r, w.tile_row + d.t0, d_b, w.dinv, w.partials,
-                             &w.sc->cnt_c, &w.sc->resnorm2, nullptr, x_readable))) return rc;
+    const double *x_use = d_x;
+    int x_use_readable = x_readable;
+    if ((rc = dist_halo_any(ctx, d, d_x, w.sc, &x_use, &x_use_readable, x_readable))) return rc;
+    if ((rc = launch_spmv<2>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, x_use, r, w.tile_row + d.t0, d_b, w.dinv, w.partials,
+                             &w.sc->cnt_c, &w.sc->resnorm2, nullptr, x_use_readable))) return rc;
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.dinv, w.partials, &w.sc->cnt_a, d.red + 1);
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, d_b, w.dinv, w.partials, &w.sc->cnt_a, d.red + 2);
     if (n > 0) {
@@ -1459,7 +1546,7 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
         static const bool prof = getenv("DKMC_DIST_PROF") != nullptr;
         static int prof_batches = 0;
         cudaEvent_t pe[33][5];
-        const bool do_prof = prof && fused && prof_batches < 3 && check_every <= 32;
+        const bool do_prof = prof && fused && prof_batches < 200 && check_every <= 32 && ds->rank == 0;
         if (do_prof) for (int a = 0; a < 33; ++a) for (int b = 0; b < 5; ++b) cudaEventCreate(&pe[a][b]);
         for (int k = 0; k < check_every && fused; ++k) {
             if (do_prof) cudaEventRecord(pe[k][0], ctx->stream);
@@ -1484,8 +1571,11 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
             double acc[4] = {0, 0, 0, 0};
             for (int k = 0; k < check_every; ++k)
                 for (int b = 0; b < 4; ++b) { float ms = 0; cudaEventElapsedTime(&ms, pe[k][b], pe[k][b + 1]); acc[b] += ms; }
-            fprintf(stderr, "rank %d n_cl %d: us per iteration: spmv %.1f update %.1f reduce_scalars %.1f direction+halo %.1f\n", ds->rank, n,
-                    1e3 * acc[0] / check_every, 1e3 * acc[1] / check_every, 1e3 * acc[2] / check_every, 1e3 * acc[3] / check_every);
+            float span = 0;
+            cudaEventElapsedTime(&span, pe[0][0], pe[check_every - 1][4]);
+            fprintf(stderr, "batch %d: us/iter: spmv %.1f update %.1f reduce %.1f direction %.1f | span %.1f\n", prof_batches,
+                    1e3 * acc[0] / check_every, 1e3 * acc[1] / check_every, 1e3 * acc[2] / check_every, 1e3 * acc[3] / check_every,
+                    1e3 * span / check_every);
             for (int a = 0; a < 33; ++a) for (int b = 0; b < 5; ++b) cudaEventDestroy(pe[a][b]);
             ++prof_batches;
         }
@@ -1527,18 +1617,21 @@ static int dist_true_residual(dkmc_ctx *ctx, int m, int nnz, const int *d_row_pt
     const int nt = d.t1 - d.t0, rows = d.rb - d.ra, vg = dist_grid(ctx, rows), n = d.n_cl;
     (void)nnz;
     int rc;
-    if ((rc = halo_exchange(ctx, d, d_x))) return rc;
+    const double *x_use = d_x;
+    int x_use_readable = 0;
+    if ((rc = dist_halo_any(ctx, d, d_x, w.sc, &x_use, &x_use_readable, 0))) return rc;
     if (nt > 0)
-        DKMC_LAUNCH(ctx, residual_dd_kernel, nt, kSpmvThreads, 0, m, d_row_ptr, d_col, d_val, d_x, d_rhs, w.dinv, w.res,
+        DKMC_LAUNCH(ctx, residual_dd_kernel, nt, kSpmvThreads, 0, m, d_row_ptr, d_col, d_val, x_use, d_rhs, w.dinv, w.res,
                     w.tile_row + d.t0, w.partials, &w.sc->cnt_d, &w.sc->resnorm2);
     if (n > 0) {
         DKMC_LAUNCH(ctx, cluster_partial_kernel, ceil_div(n, 128), 128, 0, n, d.ra, d.rb, d.seg_start, d.seg_len, d.mem_row, w.res, d.red + 4);
-        DKMC_NCCL(ncclAllReduce(d.red + 4, d.red + 4, (size_t)n, ncclDouble, ncclSum, ds->comm, ctx->stream));
+        if ((rc = dist_allreduce(ctx, d.red + 4, (size_t)n, w.sc))) return rc;
     }
     unsigned long long *mx = reinterpret_cast<unsigned long long *>(w.sc + 1);
     DKMC_CUDA(cudaMemsetAsync(mx, 0, 2 * sizeof(unsigned long long), ctx->stream));
     DKMC_LAUNCH(ctx, dist_inf_norms_kernel, vg, kVecThreads, 0, d.ra, d.rb, w.res, w.P, d.red + 4, d_x, mx);
-    DKMC_NCCL(ncclAllReduce(mx, mx, 2, ncclUint64, ncclMax, ds->comm, ctx->stream));
+    // non-negative doubles: the max of the values is the max of their bit patterns
+    if ((rc = dist_allreduce(ctx, reinterpret_cast<double *>(mx), 2, w.sc, true))) return rc;
     double hm[2] = {0.0, 0.0};
     DKMC_CUDA(cudaMemcpyAsync(hm, mx, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1882,13 +1975,30 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
     double *x = d_site_potential_boundary + NL;
     rc = dist_solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, d, o, info, m + NR);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
-    // all-gather of the solution: every rank broadcasts its rows
+    // all-gather of the solution.  Peer memory: own rows into the window, a barrier, every rank pulls
+    // the other ranks' rows from their windows, a barrier (the windows are written again in the next solve)
+    if (ds->p2p && m <= ds->m_cap && !(g_flags & 128)) {
+        P2pHalo H0;
+        memset(&H0, 0, sizeof(H0));
+        const int rows = d.rb - d.ra;
+        int grid = ceil_div(rows > 0 ? rows : 1, 256);
+        if (grid > ctx->num_sms * 4) grid = ctx->num_sms * 4;
+        DKMC_LAUNCH(ctx, p2p_scatter_rows_kernel, grid, 256, 0, d.ra, d.rb, x, ds->peers, H0, ++ds->hseq, &d.w.sc->cnt_d, &d.w.sc->pad);
+        if ((rc = dist_allreduce(ctx, d.red, 1, d.w.sc))) return rc;   // barrier
+        P2pRows R;
+        memset(&R, 0, sizeof(R));
+        R.world = ds->world;
+        for (int q = 0; q < ds->world; ++q) { R.begin[q] = plan->row_begin[q]; R.end[q] = plan->row_end[q]; }
+        DKMC_LAUNCH(ctx, p2p_pull_rows_kernel, ctx->num_sms * 4, 256, 0, ds->peers, R, x);
+        if ((rc = dist_allreduce(ctx, d.red, 1, d.w.sc))) return rc;   // barrier
+    } else {
     DKMC_NCCL(ncclGroupStart());
     for (int r = 0; r < ds->world; ++r) {
         int cnt = plan->row_end[r] - plan->row_begin[r];
         if (cnt > 0) DKMC_NCCL(ncclBroadcast(x + plan->row_begin[r], x + plan->row_begin[r], (size_t)cnt, ncclDouble, r, ds->comm, ctx->stream));
     }
     DKMC_NCCL(ncclGroupEnd());
+    }
     if (NL > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NL, 256), 256, 0, NL, -Vd / 2, d_site_potential_boundary);
     if (NR > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NR, 256), 256, 0, NR, Vd / 2, d_site_potential_boundary + (N - NR));
     DKMC_CUDA(cudaEventRecord(ctx->ev_c, ctx->stream));

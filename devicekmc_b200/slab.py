@@ -137,6 +137,11 @@ class SlabSim:
         if distributed_cg and world > 1:
             from . import _dist
             self.dcg = _dist.DistributedSolver(self)
+            if not self.dcg.p2p and os.environ.get("DKMC_P2P", "1") != "0":
+                # no peer access between these GPUs: three NCCL calls per CG iteration cost more than the
+                # partition saves at this size, so every rank solves the whole system instead
+                self.dcg.close()
+                self.dcg = None
 
     def step(self, Vd: float):
         import devicekmc_b200 as D
@@ -182,7 +187,7 @@ def bench_multi_gpu(args, metric: str, unit: str):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     el, x, y, z, lat, nc, p = bench.workload(args.workload)
     el = bench.substoichiometric(el, p)
-    s = SlabSim((el, x, y, z), p, rank, world, distributed_cg=bool(getattr(args, 'distributed_cg', False)))
+    s = SlabSim((el, x, y, z), p, rank, world, distributed_cg=not getattr(args, 'replicated_cg', False))
     stats = []
     sampler = bench.ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -225,7 +230,8 @@ def bench_multi_gpu(args, metric: str, unit: str):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "sites": s.dev.N, "nn": s.buf.nn_, "Vd": args.vd,
                            "partition": f"x-slabs over {world} ranks: rows by nnz tiles (CG), targets by site (pairwise)",
-                           "cg": "distributed" if s.dcg is not None else "replicated",
+                           "cg": ("slab-partitioned, exchange over NVLink peer memory (CUDA IPC)" if s.dcg is not None and s.dcg.p2p
+                                  else "slab-partitioned, NCCL" if s.dcg is not None else "replicated"),
                            "l2": "inputs larger than L2"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": args.steps / (ms2.item() * 1e-3), "unit": unit, "h2d_bytes_per_step": s.buf.h2d_bytes(),
