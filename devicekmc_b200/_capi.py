@@ -70,7 +70,7 @@ EXPORTS = [
     "dkmc_pairwise_pairs_evaluated", "dkmc_build_event_list",
     "dkmc_inclusive_scan", "dkmc_select_event", "dkmc_execute_kmc_step", "dkmc_kmc_step_continue",
     "dkmc_ctx_set_exact_select", "dkmc_last_event_tables", "dkmc_probe_fp64_tflops", "dkmc_spmv_tile_nnz", "dkmc_dist_unique_id", "dkmc_dist_init",
-    "dkmc_dist_finalize", "dkmc_dist_background_potential", "dkmc_dist_p2p_alloc", "dkmc_dist_p2p_open",
+    "dkmc_dist_finalize", "dkmc_dist_background_potential", "dkmc_dist_p2p_alloc", "dkmc_dist_p2p_open", "dkmc_dist_allgather_rows",
 ]
 
 _lib = None
@@ -130,6 +130,7 @@ def load() -> C.CDLL:
         lib.dkmc_dist_finalize.argtypes = [vp]
         lib.dkmc_dist_p2p_alloc.argtypes = [vp, ci, C.c_char_p]
         lib.dkmc_dist_p2p_open.argtypes = [vp, C.c_char_p]
+        lib.dkmc_dist_allgather_rows.argtypes = [vp, vp, ci, vp, vp]
         lib.dkmc_dist_background_potential.argtypes = [vp, C.POINTER(Sparsity), ci, ci, ci, cd, cd, cd, vp, vp, vp, ci, vp,
                                                        C.POINTER(DistPlan), C.POINTER(SolverOpts), C.POINTER(SolveInfo)]
         lib.dkmc_probe_fp64_tflops.argtypes = [vp, C.POINTER(cd)]

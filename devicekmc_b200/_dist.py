@@ -61,7 +61,7 @@ class DistributedSolver:
         if p2p and os.environ.get("DKMC_P2P", "1") != "0":
             # peer-memory windows: CUDA IPC handles all-gathered through torch.distributed
             hbuf = C.create_string_buffer(64)
-            ok = lib.dkmc_dist_p2p_alloc(sim.dev.ctx.h, sp.m, hbuf) == 0
+            ok = lib.dkmc_dist_p2p_alloc(sim.dev.ctx.h, sim.dev.N, hbuf) == 0   # room for a per-site array
             handles = [None] * sim.world
             dist.all_gather_object(handles, bytes(hbuf.raw) if ok else b"")
             if all(len(h) == 64 for h in handles):

@@ -1904,6 +1904,46 @@ int dkmc_dist_p2p_open(dkmc_ctx *ctx, const char *ipc_handles64) {
     return DKMC_OK;
 }
 
+int dkmc_dist_allgather_rows(dkmc_ctx *ctx, double *d_buf, int n, const int *row_begin, const int *row_end) {
+    DKMC_REQUIRE(ctx && d_buf && row_begin && row_end && n > 0, "arguments");
+    DistState *ds = dist_of(ctx);
+    DKMC_REQUIRE(ds != nullptr, "dkmc_dist_init must be called first");
+    const int me = ds->rank;
+    if (ds->p2p && n <= ds->m_cap) {
+        CgScalars *sc;
+        bool fresh = ctx->slot_ptr[S_SCALARS] == nullptr;
+        int rc;
+        if ((rc = ensure<CgScalars>(ctx, S_SCALARS, 4, &sc))) return rc;
+        if (fresh) DKMC_CUDA(cudaMemsetAsync(sc, 0, 4 * sizeof(CgScalars), ctx->stream));
+        double *scratch;
+        if ((rc = ensure<double>(ctx, S_DIST_RED, 16, &scratch))) return rc;
+        // barrier first: nobody may still be reading the windows (e.g. the tail of the previous solve)
+        if ((rc = dist_allreduce(ctx, scratch, 1, sc))) return rc;
+        P2pHalo H0;
+        memset(&H0, 0, sizeof(H0));
+        const int rows = row_end[me] - row_begin[me];
+        int grid = ceil_div(rows > 0 ? rows : 1, 256);
+        if (grid > ctx->num_sms * 4) grid = ctx->num_sms * 4;
+        DKMC_LAUNCH(ctx, p2p_scatter_rows_kernel, grid, 256, 0, row_begin[me], row_end[me], d_buf, ds->peers, H0, ++ds->hseq,
+                    &sc->cnt_d, &sc->pad);
+        if ((rc = dist_allreduce(ctx, scratch, 1, sc))) return rc;
+        P2pRows R;
+        memset(&R, 0, sizeof(R));
+        R.world = ds->world;
+        for (int q = 0; q < ds->world; ++q) { R.begin[q] = row_begin[q]; R.end[q] = row_end[q]; }
+        DKMC_LAUNCH(ctx, p2p_pull_rows_kernel, ctx->num_sms * 4, 256, 0, ds->peers, R, d_buf);
+        if ((rc = dist_allreduce(ctx, scratch, 1, sc))) return rc;
+        return DKMC_OK;
+    }
+    DKMC_NCCL(ncclGroupStart());
+    for (int r = 0; r < ds->world; ++r) {
+        int cnt = row_end[r] - row_begin[r];
+        if (cnt > 0) DKMC_NCCL(ncclBroadcast(d_buf + row_begin[r], d_buf + row_begin[r], (size_t)cnt, ncclDouble, r, ds->comm, ctx->stream));
+    }
+    DKMC_NCCL(ncclGroupEnd());
+    return DKMC_OK;
+}
+
 int dkmc_dist_finalize(dkmc_ctx *ctx) {
     DKMC_REQUIRE(ctx != nullptr, "ctx");
     DistState *ds = dist_of(ctx);

@@ -126,6 +126,8 @@ class SlabSim:
         self.buf.site_potential_charge = self._pc_full[:N]
         self.i0 = min(N, rank * self.chunk)
         self.i1 = min(N, (rank + 1) * self.chunk)
+        self._rows_b = np.array([min(N, r * self.chunk) for r in range(world)], np.int32)
+        self._rows_e = np.array([min(N, (r + 1) * self.chunk) for r in range(world)], np.int32)
         self.buf.sync_HostToGPU(self.dev)
         self.sp = self.buf.sparsity(self.nc, self.nc)
         # the pairwise kernel's share of each SM while it runs beside the CG: the fewer targets a rank
@@ -168,8 +170,13 @@ class SlabSim:
         pw_ms = C.c_double(0.0)
         check(lib.dkmc_poisson_gridless_join(dev.ctx.h, C.byref(pw_ms)))
         if self.world > 1:
-            mine = self._pc_full[self.rank * self.chunk:(self.rank + 1) * self.chunk].clone()
-            self.dist.all_gather_into_tensor(self._pc_full, mine)
+            if self.dcg is not None and self.dcg.p2p:
+                # every rank pulls the other ranks' target rows from their peer windows (no NCCL call)
+                check(lib.dkmc_dist_allgather_rows(dev.ctx.h, self._pc_full.data_ptr(), dev.N,
+                                                   self._rows_b.ctypes.data, self._rows_e.ctypes.data))
+            else:
+                mine = self._pc_full[self.rank * self.chunk:(self.rank + 1) * self.chunk].clone()
+                self.dist.all_gather_into_tensor(self._pc_full, mine)
         t = self.sim.executeKMCStep(buf, dev)
         return {"cg_iterations": info.iterations, "solve_ms": info.solve_ms, "assemble_ms": info.assemble_ms,
                 "pairwise_ms": pw_ms.value,

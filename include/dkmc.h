@@ -267,6 +267,11 @@ int dkmc_dist_finalize(dkmc_ctx *ctx);
  * with the world * 64 bytes.  Without it dkmc_dist_background_potential uses NCCL throughout. */
 int dkmc_dist_p2p_alloc(dkmc_ctx *ctx, int m, char *ipc_handle64);
 int dkmc_dist_p2p_open(dkmc_ctx *ctx, const char *ipc_handles64);
+/* all-gather of a caller array split by rows over the ranks (row_begin/row_end: HOST int[world]; rank r
+ * holds rows [row_begin[r], row_end[r]) of d_buf on entry, every rank holds all of them on return):
+ * through the peer windows when they are open and hold n doubles, else NCCL broadcasts.
+ * Asynchronous on the context's stream. */
+int dkmc_dist_allgather_rows(dkmc_ctx *ctx, double *d_buf, int n, const int *row_begin, const int *row_end);
 /* background_potential_gpu_sparse (gpu_solvers.h:139-141) over `world` GPUs; on return every rank
  * holds the full d_site_potential_boundary. */
 int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd,
