@@ -57,16 +57,21 @@ __global__ void site_class_kernel(int N, const int *__restrict__ element, const 
     int e = element[i];
     bool metal = false;
     for (int k = 0; k < num_metals; ++k) metal |= (metals[k] == e);
-    cls[i] = metal ? 1 : ((e == DKMC_VACANCY && charge[i] == 0) ? 2 : 0);
+    cls[i] = metal ? 1 : ((e == DKMC_VACANCY && charge != nullptr && charge[i] == 0) ? 2 : 0);
 }
 
-// conductance rule potential_solver.cpp:325-346: high_G iff (metal & metal) or (uncharged V & uncharged V)
-__device__ __forceinline__ double conductance(unsigned char ci, unsigned char cj, double high_G, double low_G) {
-    return (ci != 0 && ci == cj) ? high_G : low_G;
+// conductance rules.  0, background potential (potential_solver.cpp:325-346): high_G iff (metal & metal)
+// or (uncharged V & uncharged V).  1, CB-edge Laplace solve (potential_solver.cpp:58-70): high_G iff
+// either site is a metal.
+__device__ __forceinline__ bool is_high(unsigned char ci, unsigned char cj, int rule) {
+    return rule == 0 ? (ci != 0 && ci == cj) : (ci == 1 || cj == 1);
+}
+__device__ __forceinline__ double conductance(unsigned char ci, unsigned char cj, double high_G, double low_G, int rule = 0) {
+    return is_high(ci, cj, rule) ? high_G : low_G;
 }
 
 __global__ void __launch_bounds__(128) assemble_kernel(
-    int m, int N, int NL, int NR, double Vd, double high_G, double low_G,
+    int m, int N, int NL, int NR, double VL, double VR, int rule, double high_G, double low_G,
     const unsigned char *__restrict__ cls, const int *__restrict__ row_ptr, const int *__restrict__ col,
     const int *__restrict__ lrp, const int *__restrict__ lcol, const int *__restrict__ rrp,
     const int *__restrict__ rcol, double *__restrict__ val, double *__restrict__ rhs,
@@ -75,12 +80,11 @@ __global__ void __launch_bounds__(128) assemble_kernel(
     double *__restrict__ pdiag) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
-    const double VL = -Vd / 2, VR = Vd / 2;
     const unsigned char ci = cls[r + NL];
     double diag = 0.0, ksub = 0.0;
     // ascending j: left contact, interior, right contact (potential_solver.cpp:350-372)
     for (int p = lrp[r]; p < lrp[r + 1]; ++p) {
-        double G = conductance(ci, cls[lcol[p]], high_G, low_G);
+        double G = conductance(ci, cls[lcol[p]], high_G, low_G, rule);
         diag = __dadd_rn(diag, G);
         ksub = __dadd_rn(ksub, __dmul_rn(-G, VL));
     }
@@ -92,14 +96,14 @@ __global__ void __launch_bounds__(128) assemble_kernel(
         int c = col[p];
         if (c == r) { dpos = p; continue; }
         const unsigned char cj = cls[c + NL];
-        double G = conductance(ci, cj, high_G, low_G);
+        double G = conductance(ci, cj, high_G, low_G, rule);
         val[p] = -G;
-        if (pcol) pcol[p] = c | ((ci != 0 && ci == cj) ? kPackHigh : 0);           // packed CSR: column | high_G bit
-        if (code) code[p] = code_base[p] | ((ci != 0 && ci == cj) ? 0x4000 : 0);  // window-staged format: high_G bit
+        if (pcol) pcol[p] = c | (is_high(ci, cj, rule) ? kPackHigh : 0);           // packed CSR: column | high_G bit
+        if (code) code[p] = code_base[p] | (is_high(ci, cj, rule) ? 0x4000 : 0);  // window-staged format: high_G bit
         diag = __dadd_rn(diag, G);
     }
     for (int p = rrp[r]; p < rrp[r + 1]; ++p) {
-        double G = conductance(ci, cls[rcol[p] + (N - NR)], high_G, low_G);
+        double G = conductance(ci, cls[rcol[p] + (N - NR)], high_G, low_G, rule);
         diag = __dadd_rn(diag, G);
         ksub = __dadd_rn(ksub, __dmul_rn(-G, VR));
     }
@@ -1711,10 +1715,21 @@ int dkmc_spmv_window(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const 
                           nullptr, nullptr, nullptr, x_readable);
 }
 
+static int assemble_impl(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double VL, double VR, int rule,
+                         double high_G, double low_G, const int *d_site_element, const int *d_site_charge,
+                         const int *d_metals, int num_metals, double *d_val, double *d_rhs);
+
 int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd, double high_G,
                     double low_G, const int *d_site_element, const int *d_site_charge, const int *d_metals,
                     int num_metals, double *d_val, double *d_rhs) {
     DKMC_REQUIRE(ctx && sp && d_site_element && d_site_charge && d_val && d_rhs, "null pointer");
+    return assemble_impl(ctx, sp, N, NL, NR, -Vd / 2, Vd / 2, 0, high_G, low_G, d_site_element, d_site_charge, d_metals,
+                         num_metals, d_val, d_rhs);
+}
+
+static int assemble_impl(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double VL, double VR, int rule,
+                         double high_G, double low_G, const int *d_site_element, const int *d_site_charge,
+                         const int *d_metals, int num_metals, double *d_val, double *d_rhs) {
     DKMC_REQUIRE(sp->m == N - NL - NR, "sparsity does not match N, NL, NR");
     unsigned char *cls;
     double *dinv;
@@ -1739,7 +1754,7 @@ int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int N
     }
     DKMC_LAUNCH(ctx, site_class_kernel, ceil_div(N, 256), 256, 0, N, d_site_element, d_site_charge, d_metals,
                 num_metals, cls);
-    DKMC_LAUNCH(ctx, assemble_kernel, ceil_div(sp->m, 128), 128, 0, sp->m, N, NL, NR, Vd, high_G, low_G, cls,
+    DKMC_LAUNCH(ctx, assemble_kernel, ceil_div(sp->m, 128), 128, 0, sp->m, N, NL, NR, VL, VR, rule, high_G, low_G, cls,
                 sp->d_row_ptr, sp->d_col, sp->d_left_row_ptr, sp->d_left_col, sp->d_right_row_ptr, sp->d_right_col,
                 d_val, d_rhs, dinv, wf.code_base, wf.code_pos, wf.diag_pos, win_ok ? wf.blobs : nullptr, pk.pcol,
                 pk.pcol ? pk.diag : nullptr);
@@ -1837,6 +1852,47 @@ int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int
     return rc;
 }
 
+
+int dkmc_update_CB_edge_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd, double q,
+                               double high_G, double low_G, const int *d_site_element, const int *d_metals,
+                               int num_metals, double *d_site_CB_edge, const dkmc_solver_opts *opts,
+                               dkmc_solve_info *info) {
+    DKMC_REQUIRE(ctx && sp && d_site_element && d_site_CB_edge, "null pointer");
+    DKMC_REQUIRE(sp->m == N - NL - NR && sp->m > 0, "sparsity does not match N, NL, NR");
+    dkmc_solver_opts o;
+    dkmc_default_solver_opts(&o);
+    if (opts) o = *opts;
+    const int m = sp->m;
+    const double VL = q * Vd / 2, VR = -q * Vd / 2;   // potential_solver.cpp:35,41
+    double *val, *rhs;
+    CgWork w;
+    int rc;
+    if ((rc = ensure<double>(ctx, S_CG_VAL, (size_t)sp->nnz, &val))) return rc;
+    if ((rc = ensure<double>(ctx, S_CG_RHS, m, &rhs))) return rc;
+    if ((rc = cg_workspace(ctx, m, sp->nnz, sp->d_row_ptr, &w))) return rc;
+    DKMC_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    // rule 1: high_G iff either site is a metal; the charges do not enter.  No cluster coarse space:
+    // under this rule every strongly coupled set hangs on a Dirichlet contact through the metal layers.
+    if ((rc = assemble_impl(ctx, sp, N, NL, NR, VL, VR, 1, high_G, low_G, d_site_element, nullptr, d_metals, num_metals, val,
+                            rhs))) return rc;
+    DKMC_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    double *x = d_site_CB_edge + NL;
+    rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info, m + NR);
+    if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
+    if (NL > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NL, 256), 256, 0, NL, VL, d_site_CB_edge);
+    if (NR > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NR, 256), 256, 0, NR, VR, d_site_CB_edge + (N - NR));
+    DKMC_CUDA(cudaEventRecord(ctx->ev_c, ctx->stream));
+    DKMC_CUDA(cudaEventSynchronize(ctx->ev_c));
+    if (info) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ctx->ev_a, ctx->ev_b);
+        cudaEventElapsedTime(&b, ctx->ev_b, ctx->ev_c);
+        info->assemble_ms = a;
+        info->solve_ms = b;
+    }
+    if (rc == DKMC_ERR_NOT_CONVERGED) set_error("CG did not converge within max_iter=%d", o.max_iter);
+    return rc;
+}
 
 int dkmc_spmv_tile_nnz(void) { return kSpmvTile; }
 

@@ -7,6 +7,7 @@ like the reference's own flow (kmc_main.cpp:175-279):
     Device.makeSubstoichiometric      Device.cpp:202
     Device.updateCharge(gpubuf, ..)   potential_solver.cpp:142
     Device.updatePotential(..)        potential_solver.cpp:232
+    Device.setLaplacePotential(..)    potential_solver.cpp:4       CB edge, once per bias point
     KMCProcess(device, freq)          KMCProcess.cpp:17    layers, site->layer, KMC RNG
     KMCProcess.executeKMCStep(..)     KMCProcess.cpp:259
     GPUBuffers(...)                   gpu_buffers.h:73     device-resident mirror of Device
@@ -149,6 +150,7 @@ class KMCParameters:
     initial_vacancy_concentration: float = 0.05
     high_G: float = 1.0    # input_parser.cpp:392
     low_G: float = 1e-8    # input_parser.cpp:393
+    q: float = 1.60217663e-19   # input_parser.h: elementary charge [C]
     V_switch: Sequence[float] = (0.0,)
     t_switch: Sequence[float] = (1e-3,)
     restart_xyz_file: str = ""
@@ -278,6 +280,7 @@ class Device:
         self.site_potential_boundary = np.zeros(self.N, np.float64)
         self.site_potential_charge = np.zeros(self.N, np.float64)
         self.site_temperature = np.full(self.N, self.T_bg, np.float64)
+        self.site_CB_edge = np.zeros(self.N, np.float64)
         self.updateAtomLists()
 
     def updateAtomLists(self):
@@ -342,6 +345,30 @@ class Device:
                 "overlap": bool(overlap)}
 
 
+    def _set_laplace(self, gpubuf, p, Vd, opts=None):
+        lib = self.ctx.lib
+        nc = p.num_atoms_first_layer                      # potential_solver.cpp:7-8
+        sp = gpubuf.sparsity(nc, nc)
+        info = SolveInfo()
+        st = lib.dkmc_update_CB_edge_sparse(
+            self.ctx.h, C.byref(sp), self.N, nc, nc, float(Vd), float(p.q), float(p.high_G), float(p.low_G),
+            _ptr(gpubuf.site_element), _ptr(gpubuf.metal_types), gpubuf.num_metal_types_, _ptr(gpubuf.site_CB_edge),
+            C.byref(opts) if opts is not None else None, C.byref(info))
+        check(st, allow=(_capi.DKMC_ERR_NOT_CONVERGED,))
+        return {"cg_iterations": info.iterations, "cg_est_error": info.est_error, "cg_refinements": info.refinements,
+                "cg_converged": st == _capi.DKMC_OK, "assemble_ms": info.assemble_ms, "solve_ms": info.solve_ms}
+
+    def setLaplacePotential(self, gpubuf: "GPUBuffers", p: KMCParameters, Vd: float,
+                            opts: Optional[SolverOpts] = None) -> dict:
+        """potential_solver.cpp:4-139, GPU branch (:10-19): host -> device sync, the CB-edge solve
+        (update_CB_edge_gpu_sparse), device -> host sync.  Called once per bias point
+        (kmc_main.cpp:160)."""
+        gpubuf.sync_HostToGPU(self, also=("site_CB_edge",))
+        out = self._set_laplace(gpubuf, p, Vd, opts)
+        gpubuf.sync_GPUToHost(self, also=("site_CB_edge",))
+        return out
+
+
 class GPUBuffers:
     """Device-resident mirror of Device (gpu_buffers.h:12-162): one array per site attribute, the
     1-element scalars the reference keeps on the device, and the CSR index buffers of K."""
@@ -363,6 +390,7 @@ class GPUBuffers:
         self.site_potential_boundary = torch.zeros(self.N_, **f64)
         self.site_potential_charge = torch.zeros(self.N_, **f64)
         self.site_temperature = torch.full((self.N_,), device.T_bg, **f64)
+        self.site_CB_edge = torch.zeros(self.N_, **f64)
         self.metal_types = torch.tensor(list(metals), dtype=torch.int32, device=dev)
         self.sigma = torch.tensor([device.sigma], **f64)
         self.k = torch.tensor([device.k], **f64)
@@ -404,16 +432,17 @@ class GPUBuffers:
             self._pin[name] = ent
         return ent[0]
 
-    def sync_HostToGPU(self, device: Device):
-        """gpu_buffers.cpp:10-37"""
-        for name in self._SYNCED:
+    def sync_HostToGPU(self, device: Device, also=()):
+        """gpu_buffers.cpp:10-37.  The per-step arrays; `also` adds the per-bias-point ones
+        (site_CB_edge), which the hot path never touches."""
+        for name in self._SYNCED + tuple(also):
             getattr(self, name).copy_(self._pinned(device, name), non_blocking=True)
         self.T_bg.fill_(device.T_bg)
 
-    def sync_GPUToHost(self, device: Device):
+    def sync_GPUToHost(self, device: Device, also=()):
         """gpu_buffers.cpp:39-55"""
         torch = _torch()
-        for name in self._SYNCED:
+        for name in self._SYNCED + tuple(also):
             self._pinned(device, name).copy_(getattr(self, name), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 

@@ -119,6 +119,25 @@ void background_potential_gpu_sparse(cublasHandle_t, cusolverDnHandle_t, GPUBuff
     std::cout << "# CG steps: " << info.iterations << "\n";  // iterative_solvers_gpu.cu:457
 }
 
+// gpu_solvers.h:121-123.  Called once per bias point from Device::setLaplacePotential
+// (potential_solver.cpp:15) when solve_current = 1.  The reference solves in volts and scales the
+// whole vector by eV_to_J = 1.60217663e-19 afterwards (potential_solver_gpu.cu:672); the system is
+// linear, so the contacts carry the factor here.
+void update_CB_edge_gpu_sparse(cublasHandle_t, cusolverDnHandle_t, GPUBuffers &gpubuf, const int N,
+                               const int N_left_tot, const int N_right_tot, const double d_Vd, const int pbc,
+                               const double d_high_G, const double d_low_G, const double nn_dist,
+                               const int num_metals) {
+    (void)pbc; (void)nn_dist;
+    dkmc_sparsity sp = sparsity_of(gpubuf, N - N_left_tot - N_right_tot);
+    dkmc_solve_info info = {};
+    int st = dkmc_update_CB_edge_sparse(ctx(), &sp, N, N_left_tot, N_right_tot, d_Vd, 1.60217663e-19, d_high_G, d_low_G,
+                                        reinterpret_cast<const int *>(gpubuf.site_element),
+                                        reinterpret_cast<const int *>(gpubuf.metal_types), num_metals,
+                                        gpubuf.site_CB_edge, nullptr, &info);
+    report(st, "update_CB_edge_gpu_sparse");
+    std::cout << "# CG steps: " << info.iterations << "\n";  // iterative_solvers_gpu.cu:457
+}
+
 // gpu_solvers.h:144-147
 void poisson_gridless_gpu(const int num_atoms_contact, const int pbc, const int N, const double *lattice,
                           const double *sigma, const double *k, const double *posx, const double *posy,

@@ -123,6 +123,17 @@ int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int
                                      double *d_site_potential_boundary,
                                      const dkmc_solver_opts *opts, dkmc_solve_info *info);
 
+/* ---- conduction-band edge.  update_CB_edge_gpu_sparse, gpu_solvers.h:121-123
+ * (potential_solver_gpu.cu:595-694; CPU semantics Device::setLaplacePotential,
+ * potential_solver.cpp:4-139): the same Kirchhoff system with the rule "high_G iff either site is a
+ * metal", contacts at +q Vd / 2 (first NL sites) and -q Vd / 2 (last NR sites); called once per bias
+ * point.  Same assembly kernel and refined PCG (plain Jacobi: no vacancy clusters under this rule),
+ * warm-started from d_site_CB_edge. */
+int dkmc_update_CB_edge_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd,
+                               double q, double high_G, double low_G, const int *d_site_element,
+                               const int *d_metals, int num_metals, double *d_site_CB_edge,
+                               const dkmc_solver_opts *opts, dkmc_solve_info *info);
+
 /* building blocks of a4/a5, exported for parity tests and the roofline measurements */
 int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double Vd,
                     double high_G, double low_G, const int *d_site_element, const int *d_site_charge,

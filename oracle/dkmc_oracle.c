@@ -280,21 +280,38 @@ void orc_csr_fill(int N, int nn, const int *neigh_idx, int NL, int NR, const int
 }
 
 /* ------------------------------------------------------------------ K assembly */
+/* rule 0: background potential, potential_solver.cpp:325-346 — high_G iff (metal & metal) or
+ *         (uncharged vacancy & uncharged vacancy);
+ * rule 1: CB-edge Laplace solve, potential_solver.cpp:58-70 — high_G iff (metal || metal). */
+static int g_rule = 0;
+#pragma omp threadprivate(g_rule)
 static double conductance(int ei, int qi, int ej, int qj, const int *metals, int nm,
                           double high_G, double low_G) {
     int metal1 = in_list(metals, nm, ei), metal2 = in_list(metals, nm, ej);
+    if (g_rule == 1) return (metal1 || metal2) ? high_G : low_G;
     int cv1 = (ei == ORC_VACANCY && qi == 0), cv2 = (ej == ORC_VACANCY && qj == 0);
     return ((metal1 && metal2) || (cv1 && cv2)) ? high_G : low_G;
 }
+
+static void assemble_rule(int rule, double VL, double VR, int N, int nn, const int *neigh_idx, int NL, int NR,
+                          const int *element, const int *charge, const int *metals, int num_metals, double high_G,
+                          double low_G, const int *row_ptr, const int *col, double *val, double *rhs);
 
 void orc_assemble_K(int N, int nn, const int *neigh_idx, int NL, int NR, const int *element,
                     const int *charge, const int *metals, int num_metals, double high_G,
                     double low_G, double Vd, const int *row_ptr, const int *col, double *val,
                     double *rhs) {
+    assemble_rule(0, -Vd / 2, Vd / 2, N, nn, neigh_idx, NL, NR, element, charge, metals, num_metals, high_G, low_G,
+                  row_ptr, col, val, rhs);
+}
+
+static void assemble_rule(int rule, double VL, double VR, int N, int nn, const int *neigh_idx, int NL, int NR,
+                          const int *element, const int *charge, const int *metals, int num_metals, double high_G,
+                          double low_G, const int *row_ptr, const int *col, double *val, double *rhs) {
     int m = N - NL - NR;
-    double VL = -Vd / 2, VR = Vd / 2;
 #pragma omp parallel for
     for (int r = 0; r < m; ++r) {
+        g_rule = rule;
         int i = r + NL;
         const int *row = neigh_idx + (size_t)i * nn;
         /* diagonal: K[i][i] += -1*K[i][j] over ascending j (zeros add exactly), :350-359 */
@@ -437,6 +454,31 @@ void orc_background_potential(int N, int nn, const int *neigh_idx, int NL, int N
     for (int i = 0; i < NL; ++i) site_potential_boundary[i] = -Vd / 2;
     for (int i = N - NR; i < N; ++i) site_potential_boundary[i] = Vd / 2;
     free(rp); free(lrp); free(rrp); free(ci); free(lci); free(rci); free(val); free(rhs);
+}
+
+/* Device::setLaplacePotential, CPU branch (potential_solver.cpp:4-139): the same Kirchhoff system with
+ * the rule "high_G iff either site is a metal", contacts at +q Vd / 2 (left) and -q Vd / 2 (right);
+ * site_CB_edge = contact values | -inv(D) Ksub.  `charge` does not enter. */
+void orc_laplace_cb_edge(int N, int nn, const int *neigh_idx, int NL, int NR, const int *element,
+                         const int *metals, int num_metals, double high_G, double low_G, double Vd,
+                         double q, double *site_CB_edge, double tol, int max_iter, int refine,
+                         double *info) {
+    int m = N - NL - NR;
+    int *rp = (int *)malloc(sizeof(int) * (m + 1)), *lrp = (int *)malloc(sizeof(int) * (m + 1)),
+        *rrp = (int *)malloc(sizeof(int) * (m + 1));
+    orc_csr_row_ptr(N, nn, neigh_idx, NL, NR, rp, lrp, rrp);
+    int *ci = (int *)malloc(sizeof(int) * (size_t)(rp[m] + 1)), *lci = (int *)malloc(sizeof(int) * (size_t)(lrp[m] + 1)),
+        *rci = (int *)malloc(sizeof(int) * (size_t)(rrp[m] + 1));
+    orc_csr_fill(N, nn, neigh_idx, NL, NR, rp, ci, lrp, lci, rrp, rci);
+    double *val = (double *)malloc(sizeof(double) * (size_t)rp[m]), *rhs = (double *)malloc(sizeof(double) * m);
+    int *zero_charge = (int *)calloc((size_t)N, sizeof(int));
+    const double VL = q * Vd / 2, VR = -q * Vd / 2;
+    assemble_rule(1, VL, VR, N, nn, neigh_idx, NL, NR, element, zero_charge, metals, num_metals, high_G, low_G, rp, ci,
+                  val, rhs);
+    orc_solve(m, rp, ci, val, rhs, site_CB_edge + NL, tol, max_iter, refine, info);
+    for (int i = 0; i < NL; ++i) site_CB_edge[i] = VL;
+    for (int i = N - NR; i < N; ++i) site_CB_edge[i] = VR;
+    free(rp); free(lrp); free(rrp); free(ci); free(lci); free(rci); free(val); free(rhs); free(zero_charge);
 }
 
 /* ------------------------------------------------------------------ pairwise Coulomb */

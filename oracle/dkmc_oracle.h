@@ -78,6 +78,10 @@ int orc_solve(int m, const int *row_ptr, const int *col, const double *val, cons
               double *x, double tol, int max_iter, int refine, double *info);
 
 /* convenience: assemble + solve + scatter with Dirichlet contacts, potential_solver.cpp:389-403 */
+void orc_laplace_cb_edge(int N, int nn, const int *neigh_idx, int NL, int NR, const int *element,
+                         const int *metals, int num_metals, double high_G, double low_G, double Vd,
+                         double q, double *site_CB_edge, double tol, int max_iter, int refine,
+                         double *info);
 void orc_background_potential(int N, int nn, const int *neigh_idx, int NL, int NR,
                               const int *element, const int *charge, const int *metals,
                               int num_metals, double high_G, double low_G, double Vd,

@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY — link-time stubs for the reference GPU entry points that are OUT OF
-// SCOPE of devicekmc-b200 (current solver, heat solver, CB-edge solve, dense-LU potential;
+// SCOPE of devicekmc-b200 (current solver, heat solver, dense-LU potential;
 // SURVEY.md §2 rows 14/15, §8f).  They let the unmodified reference host (kmc_main.cpp ...) link
 // against our shim for the drop-in check; reaching one of them aborts with a clear message.
 #include "gpu_solvers.h"
@@ -14,10 +14,6 @@ static void out_of_scope(const char *name) {
 }
 
 extern "C" {
-void update_CB_edge_gpu_sparse(cublasHandle_t, cusolverDnHandle_t, GPUBuffers &, const int, const int, const int,
-                               const double, const int, const double, const double, const double, const int) {
-    out_of_scope("update_CB_edge_gpu_sparse");
-}
 void background_potential_gpu(cusolverDnHandle_t, GPUBuffers &, const int, const int, const int, const double, const int,
                               const double, const double, const double, const int, int) {
     out_of_scope("background_potential_gpu (dense LU variant)");

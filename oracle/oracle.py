@@ -128,6 +128,19 @@ def background_potential(neigh_idx, NL, NR, element, charge, metals, high_G, low
     return phi, info
 
 
+def laplace_cb_edge(neigh_idx, NL, NR, element, metals, high_G, low_G, Vd, q=1.60217663e-19, phi0=None,
+                    tol=1e-13, max_iter=20000, refine=3):
+    """Device::setLaplacePotential (potential_solver.cpp:4-139), sparse restatement"""
+    nb, el, me = _i32(neigh_idx), _i32(element), _i32(metals)
+    N, nn = nb.shape
+    phi = np.zeros(N) if phi0 is None else _f64(phi0).copy()
+    info = np.zeros(3)
+    lib().orc_laplace_cb_edge(N, nn, _p(nb), NL, NR, _p(el), _p(me), len(me), C.c_double(high_G), C.c_double(low_G),
+                              C.c_double(Vd), C.c_double(q), _p(phi), C.c_double(tol), int(max_iter), int(refine),
+                              _p(info))
+    return phi, info
+
+
 def poisson_gridless(x, y, z, lattice, pbc, charge, sigma, k, rows=None):
     x, y, z, lat, q = _f64(x), _f64(y), _f64(z), _f64(lattice), _i32(charge)
     N = len(x)

@@ -166,6 +166,17 @@ void ref_background_potential(void *h, double Vd, int n_contact) {
                                  s->p->low_G, s->p->metals, 0);
 }
 
+// Device::setLaplacePotential, CPU branch (potential_solver.cpp:4-139): fills site_CB_edge.
+// It sizes the contacts by num_atoms_first_layer (:7-8).
+void ref_laplace_cb_edge(void *h, double Vd) {
+    auto *s = static_cast<RefSim *>(h);
+    s->dev->setLaplacePotential(nullptr, nullptr, s->gpubuf, *s->p, Vd);
+}
+void ref_get_cb_edge(void *h, double *out) {
+    auto *s = static_cast<RefSim *>(h);
+    std::memcpy(out, s->dev->site_CB_edge.data(), s->dev->N * sizeof(double));
+}
+
 // Device::poisson_gridless (potential_solver.cpp:412-432)
 void ref_poisson_gridless(void *h) {
     auto *s = static_cast<RefSim *>(h);

@@ -131,6 +131,12 @@ class RefSim:
     def background_potential(self, Vd: float, n_contact: int = 0):
         self._lib.ref_background_potential(self._h, float(Vd), int(n_contact))
 
+    def laplace_cb_edge(self, Vd: float):
+        """Device::setLaplacePotential (CPU branch): returns site_CB_edge"""
+        self._lib.ref_laplace_cb_edge.argtypes = [C.c_void_p, C.c_double]
+        self._lib.ref_laplace_cb_edge(self._h, float(Vd))
+        return self._get("ref_get_cb_edge", self.N, np.float64)
+
     def poisson_gridless(self):
         self._lib.ref_poisson_gridless(self._h)
 

@@ -11,6 +11,8 @@ rnd_seed_kmc = 1, CPU build, 1 process):
   s_traj_ramp.npz  the kmc_main.cpp:136-279 loop on the shipped V_switch ramp, first 12 KMC steps:
                    per step Vd, executed (i, j) pairs, step time, sha256 of site_element/charge
   s_traj_6V.npz    the same loop at constant Vd = 6 V, 6 KMC steps (many events per step)
+  s_cb_edge.npz    Device::setLaplacePotential (CPU branch, potential_solver.cpp:4-139) at Vd = 1.5 V:
+                   site_CB_edge of all sites
 """
 import hashlib
 import os
@@ -60,6 +62,14 @@ def step0():
     print("step0 written", len(nz), "events")
 
 
+def cb_edge():
+    s = new_sim()
+    Vd = 1.5
+    cb = s.laplace_cb_edge(Vd)
+    np.savez_compressed(os.path.join(OUT, "s_cb_edge.npz"), Vd=Vd, n_contact=s.num_atoms_first_layer, cb_edge=cb)
+    print("cb_edge written", cb[:2], cb[-2:])
+
+
 def trajectory(name, schedule, nsteps):
     """schedule: list of (Vd, t) bias points as in kmc_main.cpp:136-279"""
     s = new_sim()
@@ -92,9 +102,11 @@ def trajectory(name, schedule, nsteps):
 if __name__ == "__main__":
     import devicekmc_b200.host as H
     p = H.KMCParameters.from_file(REF + "parameters.txt")
-    which = sys.argv[1:] or ["step0", "ramp", "6V"]
+    which = sys.argv[1:] or ["step0", "ramp", "6V", "cb_edge"]
     if "step0" in which:
         step0()
+    if "cb_edge" in which:
+        cb_edge()
     if "ramp" in which:
         trajectory("s_traj_ramp.npz", list(zip(p.V_switch, p.t_switch)), 12)
     if "6V" in which:

@@ -85,6 +85,26 @@ def test_oracle_background_potential_vs_reference_dgesv(base_case, golden_step0,
     assert i_orc[2] <= i_ref[2]
 
 
+def test_oracle_cb_edge_vs_reference_dgesv(base_case, graph, O):
+    """SURVEY 8f-3: Device::setLaplacePotential (potential_solver.cpp:4-139), the `metal || metal`
+    rule and the +-q Vd / 2 contacts, against the fixture written by the reference's CPU build.
+    No vacancy clusters under this rule, so the reference's dgesv is accurate here (cond ~ 1e3)."""
+    g = np.load(os.path.join(GOLDEN, "s_cb_edge.npz"))
+    nb, nn = graph
+    p = base_case["p"]
+    nc = int(g["n_contact"])
+    cb, info = O.laplace_cb_edge(nb, nc, nc, base_case["element"], p.metals, p.high_G, p.low_G, float(g["Vd"]))
+    ref = g["cb_edge"]
+    assert np.array_equal(cb[:nc], ref[:nc]) and np.array_equal(cb[-nc:], ref[-nc:])   # contacts: +-q Vd / 2
+    assert cb[0] == 1.60217663e-19 * float(g["Vd"]) / 2 and cb[-1] == -cb[0]
+    assert np.abs(cb - ref).max() / np.abs(ref).max() <= 1e-12
+    # the charges do not enter: vacancies (uncharged or not) change nothing
+    el2 = base_case["element"].copy()
+    el2[el2 == 3] = 2
+    cb2, _ = O.laplace_cb_edge(nb, nc, nc, el2, p.metals, p.high_G, p.low_G, float(g["Vd"]))
+    assert np.array_equal(cb, cb2)
+
+
 def test_oracle_rate_table_bit_exact_vs_reference(base_case, golden_step0, graph, O):
     nb, nn = graph
     p = base_case["p"]

@@ -234,6 +234,34 @@ def test_background_potential_cluster_preconditioner(sim0, O, torch):
         buf.sync_HostToGPU(dev)
 
 
+# ------------------------------------------------------------------ 8f-3 CB-edge Laplace solve
+def test_cb_edge_laplace(sim0, O, torch):
+    """Device::setLaplacePotential / update_CB_edge_gpu_sparse: `metal || metal` rule, contacts at
+    +-q Vd / 2, against the oracle and the fixture written by the reference's CPU build"""
+    from conftest import GOLDEN
+    p, dev, sim, buf = sim0
+    g = np.load(os.path.join(GOLDEN, "s_cb_edge.npz"))
+    Vd, nc = float(g["Vd"]), int(g["n_contact"])
+    assert nc == p.num_atoms_first_layer
+    dev.site_CB_edge[...] = 0.0
+    out = dev.setLaplacePotential(buf, p, Vd)
+    assert out["cg_converged"]
+    cb = np.array(dev.site_CB_edge)                                    # synced back to the host, as the reference does
+    assert np.array_equal(cb, buf.site_CB_edge.cpu().numpy())
+    assert np.array_equal(cb[:nc], np.full(nc, p.q * Vd / 2)) and np.array_equal(cb[-nc:], np.full(nc, -p.q * Vd / 2))
+    ref, _ = O.laplace_cb_edge(dev.neigh_idx.reshape(dev.N, -1), nc, nc, dev.site_element, p.metals, p.high_G, p.low_G, Vd)
+    assert rel_inf(cb, ref) <= TOL
+    assert rel_inf(cb, g["cb_edge"]) <= TOL
+    big = np.abs(ref) > 1e-3 * np.abs(ref).max()
+    assert (np.abs(cb[big] - ref[big]) / np.abs(ref[big])).max() <= TOL
+    # next bias point: warm start from the previous one (the reference's v_soln, potential_solver_gpu.cu:648)
+    out2 = dev.setLaplacePotential(buf, p, -2.0 * Vd)
+    assert out2["cg_converged"]
+    assert rel_inf(np.array(dev.site_CB_edge), -2.0 * ref) <= TOL
+    # the other per-step arrays are untouched by the bias-point solve
+    buf.sync_HostToGPU(dev)
+
+
 # ------------------------------------------------------------------ a6 pairwise
 @pytest.mark.parametrize("pbc", [0, 1])
 def test_poisson_gridless(base_case, O, golden_step0, torch, pbc):
