@@ -327,6 +327,31 @@ int dkmc_neighbor_fill(dkmc_ctx *ctx, int N, const double *d_x, const double *d_
     return DKMC_OK;
 }
 
+// the same builder for HOST arrays, for a host class (the reference's Device) that keeps
+// positions and the neighbour table in host memory.  One upload of the positions, count + fill on
+// the device, one download of the table.
+int dkmc_neighbor_table_host(dkmc_ctx *ctx, int N, const double *h_x, const double *h_y, const double *h_z,
+                             const double *lattice, int pbc, double nn_dist, int *max_nn, int *h_neigh_idx) {
+    DKMC_REQUIRE(ctx && h_x && h_y && h_z && lattice && max_nn, "null pointer");
+    DKMC_REQUIRE(N > 0 && nn_dist > 0, "N and nn_dist must be positive");
+    double *d_pos;
+    int rc;
+    if ((rc = ensure<double>(ctx, S_NB_HOSTPOS, (size_t)3 * N, &d_pos))) return rc;
+    double *d_x = d_pos, *d_y = d_pos + N, *d_z = d_pos + 2 * (size_t)N;
+    DKMC_CUDA(cudaMemcpyAsync(d_x, h_x, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    DKMC_CUDA(cudaMemcpyAsync(d_y, h_y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    DKMC_CUDA(cudaMemcpyAsync(d_z, h_z, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = dkmc_neighbor_count(ctx, N, d_x, d_y, d_z, lattice, pbc, nn_dist, max_nn))) return rc;
+    if (!h_neigh_idx || *max_nn == 0) return DKMC_OK;
+    int *d_tab;
+    const size_t cells = (size_t)N * (size_t)*max_nn;
+    if ((rc = ensure<int>(ctx, S_NB_HOSTTAB, cells, &d_tab))) return rc;
+    if ((rc = dkmc_neighbor_fill(ctx, N, d_x, d_y, d_z, lattice, pbc, nn_dist, *max_nn, d_tab))) return rc;
+    DKMC_CUDA(cudaMemcpyAsync(h_neigh_idx, d_tab, sizeof(int) * cells, cudaMemcpyDeviceToHost, ctx->stream));
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DKMC_OK;
+}
+
 int dkmc_initialize_sparsity(dkmc_ctx *ctx, int N, int nn, const int *d_neigh_idx, int NL, int NR,
                              dkmc_sparsity *out) {
     DKMC_REQUIRE(ctx && d_neigh_idx && out, "null pointer");

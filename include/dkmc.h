@@ -73,6 +73,13 @@ int dkmc_neighbor_count(dkmc_ctx *ctx, int N, const double *d_x, const double *d
 int dkmc_neighbor_fill(dkmc_ctx *ctx, int N, const double *d_x, const double *d_y, const double *d_z,
                        const double *lattice, int pbc, double nn_dist, int nn, int *d_neigh_idx);
 
+/* the same builder for HOST arrays (h_x/h_y/h_z in, h_neigh_idx[N * *max_nn] out), so
+ * that a host class which keeps both in host memory — the reference's Device — can replace its
+ * O(N^2) loop (Device.cpp:98-136) with one call.  h_neigh_idx == NULL: only *max_nn is written; the
+ * caller then sizes the table and calls again.  Shim: devicekmc_b200/shim/device_setup_shim.cpp. */
+int dkmc_neighbor_table_host(dkmc_ctx *ctx, int N, const double *h_x, const double *h_y, const double *h_z,
+                             const double *lattice, int pbc, double nn_dist, int *max_nn, int *h_neigh_idx);
+
 /* ---- a2: CSR structure of K.  initialize_sparsity, gpu_solvers.h:43
  * (iterative_solvers_gpu.cu:96-109 -> Assemble_K_sparsity :2158-2208).  The arrays are
  * allocated by the library (as the reference's `int **` out-parameters are) and have the
