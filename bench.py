@@ -255,6 +255,21 @@ def gpu_arm(args):
         "note": "opt-in: |delta phi_c| < 1e-21 of max|phi_c|; changes the work of the pairwise stage, so it is not the headline"}}
     check(dev.ctx.lib.dkmc_ctx_set_pairwise_cutoff(dev.ctx.h, 0.0))
 
+    # ---- variant (NOT the headline): phi_c updated by the charge differences since the previous step
+    dev.ctx.set_pairwise_incremental(32)
+    step()                                   # the first call of the mode is a full sum
+    e0.record()
+    vstats = [step() for _ in range(args.steps)]
+    e1.record(); e1.synchronize()
+    variant["pairwise_incremental"] = {
+        "value": args.steps / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
+        "potential_ms": float(np.median([s["potential_ms"] for s in vstats])),
+        "pairwise_ms": float(np.median([s["pairwise_ms"] for s in vstats])),
+        "events": [s["events"] for s in vstats],
+        "note": "opt-in (SURVEY 8f-2): O(N * n_changed) sum of the charge differences, full sum every 32nd step; "
+                "norm-wise 1e-13, changes the work of the pairwise stage, so it is not the headline"}
+    dev.ctx.set_pairwise_incremental(0)
+
     # ---- rooflines, measured live with CUDA events on the launching stream
     lib = dev.ctx.lib
     hbm_peak, peak_src = measured_peaks()

@@ -52,7 +52,7 @@ enum Slot : int {
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
     S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_PCOL, S_CG_PDIAG, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
-    S_NB_HOSTPOS, S_NB_HOSTTAB,
+    S_NB_HOSTPOS, S_NB_HOSTTAB, S_PW_PREVQ, S_PW_DQ,
     S_LAST
 };
 static_assert(S_LAST <= kNumSlots, "increase kNumSlots");
@@ -139,6 +139,15 @@ struct dkmc_ctx {
     int pw_use_cells = 1;            // skip sources beyond the distance where erfc is exactly 0 (non-periodic devices)
     struct { const double *d_x = nullptr, *d_sigma = nullptr; const void *box = nullptr; int N = 0; double cutoff_sigmas = 0.0; } pw_grid;
     double pw_cutoff_sigmas = 0.0;   // 0: exact; > 0: truncate the pairwise sum at this many sigma (opt-in)
+    // opt-in incremental update of phi_c: only the sites whose charge changed since the last
+    // call are summed, phi_c += delta; a full sum every `refresh_every` calls bounds the rounding drift
+    struct {
+        int refresh_every = 0;           // 0: off
+        int since_full = 0;
+        bool valid = false;              // prev_charge mirrors the charges d_out was computed from
+        const int *d_charge = nullptr; const double *d_out = nullptr; int N = 0, row_begin = 0, row_end = 0, pbc = 0;
+        long long full_sums = 0, delta_sums = 0;
+    } pw_inc;
     int pw_side_threads = 128;
     int pw_side_blocks_per_sm = 3;   // residency of the pairwise kernel while it shares the SMs with the CG
 };

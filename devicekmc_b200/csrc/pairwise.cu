@@ -73,6 +73,15 @@ __global__ void __launch_bounds__(kCompactBlock) charged_scatter_kernel(
     if (blockIdx.x == 0 && threadIdx.x == 0) *total = block_incl[nblocks - 1];
 }
 
+// 8f-2: dq = q - prev, prev = q.  With prev == nullptr-like first use the caller runs a full sum instead.
+__global__ void pw_delta_kernel(int N, const int *__restrict__ charge, int *__restrict__ prev, int *__restrict__ dq) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int q = charge[i];
+    dq[i] = q - prev[i];
+    prev[i] = q;
+}
+
 // ---- branch-free FP64 building blocks (MUFU seed + one third-order Newton step)
 __device__ __forceinline__ double rsqrt_fast(double a) {
     double y;
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(kPwMaxThreads) pairwise_kernel(
     int row_begin, int row_end, const double *__restrict__ x, const double *__restrict__ y,
     const double *__restrict__ z, const int *__restrict__ n_src_ptr, const ChargedSite *__restrict__ src,
     const int *__restrict__ src_idx, const double *__restrict__ lattice, const double *__restrict__ sigma_ptr,
-    const double *__restrict__ k_ptr, int *tile_counter, int *sm_count, int sm_quota, double *__restrict__ out) {
+    const double *__restrict__ k_ptr, int *tile_counter, int *sm_count, int sm_quota, int accumulate, double *out) {
     __shared__ ChargedSite tile[kPwTile];
     __shared__ int tile_idx[kPwTile];
     __shared__ int s_tile;
@@ -204,8 +213,9 @@ __global__ void __launch_bounds__(kPwMaxThreads) pairwise_kernel(
             }
         }
         // rinv is in 1/Angstrom: 1e10 converts to 1/m
-        if (va) out[ia] = (a0 + a1) * (kc * kElementaryCharge * 1e10);
-        if (vb) out[ib] = (b0 + b1) * (kc * kElementaryCharge * 1e10);
+        // accumulate: the sources are charge DIFFERENCES and out holds the previous potential (8f-2)
+        if (va) { const double v = (a0 + a1) * (kc * kElementaryCharge * 1e10); out[ia] = accumulate ? out[ia] + v : v; }
+        if (vb) { const double v = (b0 + b1) * (kc * kElementaryCharge * 1e10); out[ib] = accumulate ? out[ib] + v : v; }
     }
 }
 
@@ -344,7 +354,7 @@ __global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
     const PwGrid *__restrict__ gp, const int *__restrict__ cell_start, const ChargedSite *__restrict__ src,
     const int *__restrict__ src_idx, const double *__restrict__ sigma_ptr, const double *__restrict__ k_ptr,
     int *tile_counter, int *sm_count, int sm_quota, unsigned sm_quota_linger_ns, unsigned long long *pair_counter,
-    double *__restrict__ out) {
+    int accumulate, double *out) {
     __shared__ int s_tile;
     if (sm_count != nullptr) {
         if (threadIdx.x == 0) {
@@ -453,8 +463,9 @@ __global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
             }
         }
         // rinv is in 1/Angstrom: 1e10 converts to 1/m
-        if (va) out[ia] = (a0 + a1) * (kc * kElementaryCharge * 1e10);
-        if (vb) out[ib] = (b0 + b1) * (kc * kElementaryCharge * 1e10);
+        // accumulate: the sources are charge DIFFERENCES and out holds the previous potential (8f-2)
+        if (va) { const double v = (a0 + a1) * (kc * kElementaryCharge * 1e10); out[ia] = accumulate ? out[ia] + v : v; }
+        if (vb) { const double v = (b0 + b1) * (kc * kElementaryCharge * 1e10); out[ib] = accumulate ? out[ib] + v : v; }
     }
     if (pair_counter != nullptr) {   // pairs evaluated, for the roofline
         for (int o = 16; o > 0; o >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o);
@@ -549,7 +560,7 @@ static int pairwise_prepare(dkmc_ctx *ctx, int N, const double *d_x, const doubl
 static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm, int threads, bool shared_sms, int pbc, int row_begin, int row_end,
                            const double *d_lattice, const double *d_sigma, const double *d_k, const double *d_x,
                            const double *d_y, const double *d_z, const ChargedSite *src, const int *src_idx,
-                           const int *total, int *tile_counter, double *d_out, const PwCells *cells) {
+                           const int *total, int *tile_counter, double *d_out, const PwCells *cells, int accumulate = 0) {
     if (cells) {  // one target per thread
         int grid = ctx->num_sms * blocks_per_sm;
         int *sm_count = nullptr;
@@ -568,7 +579,7 @@ static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm
         static const int pad_smem = [] { const char *e = getenv("DKMC_PW_PAD_SMEM"); return e ? atoi(e) : 16384; }();
         DKMC_LAUNCH_ON(ctx, stream, pairwise_cells_kernel, grid, threads, pad_smem, row_begin, row_end, d_x, d_y, d_z, cells->grid,
                        cells->cell_start, cells->src, cells->src_idx, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm,
-                       pw_linger_ns(), cells->pair_counter, d_out);
+                       pw_linger_ns(), cells->pair_counter, accumulate, d_out);
         if (shared_sms && pw_gate_enabled()) DKMC_LAUNCH(ctx, pw_gate_kernel, 1, 1, 0, sm_count + 256, grid);
         return DKMC_OK;
     }
@@ -584,12 +595,43 @@ static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm
     }
     if (pbc) {
         DKMC_LAUNCH_ON(ctx, stream, pairwise_kernel<true>, grid, threads, 0, row_begin, row_end, d_x, d_y, d_z, total,
-                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm, d_out);
+                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm, accumulate, d_out);
     } else {
         DKMC_LAUNCH_ON(ctx, stream, pairwise_kernel<false>, grid, threads, 0, row_begin, row_end, d_x, d_y, d_z, total,
-                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm, d_out);
+                       src, src_idx, d_lattice, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm, accumulate, d_out);
     }
     if (shared_sms && pw_gate_enabled()) DKMC_LAUNCH(ctx, pw_gate_kernel, 1, 1, 0, sm_count + 256, grid);
+    return DKMC_OK;
+}
+
+// 8f-2 (opt-in).  Decides between a full sum and an update by the charge differences since the
+// previous call on the same arrays.  Returns the charge array the sum has to run over (the charges
+// themselves, or the differences) and whether the kernel accumulates into d_out.
+static int pairwise_incremental(dkmc_ctx *ctx, int pbc, int N, const int *d_site_charge, int row_begin, int row_end,
+                                const double *d_out, const int **charge_for_sum, int *accumulate) {
+    *charge_for_sum = d_site_charge;
+    *accumulate = 0;
+    auto &inc = ctx->pw_inc;
+    if (inc.refresh_every <= 0) { inc.valid = false; return DKMC_OK; }
+    int *prev, *dq;
+    int rc;
+    if ((rc = ensure<int>(ctx, S_PW_PREVQ, (size_t)N, &prev))) return rc;
+    if ((rc = ensure<int>(ctx, S_PW_DQ, (size_t)N, &dq))) return rc;
+    const bool same = inc.valid && inc.d_charge == d_site_charge && inc.d_out == d_out && inc.N == N &&
+                      inc.row_begin == row_begin && inc.row_end == row_end && inc.pbc == pbc;
+    if (same && inc.since_full + 1 < inc.refresh_every) {
+        DKMC_LAUNCH(ctx, pw_delta_kernel, ceil_div(N, 256), 256, 0, N, d_site_charge, prev, dq);
+        *charge_for_sum = dq;
+        *accumulate = 1;
+        ++inc.since_full;
+        ++inc.delta_sums;
+        return DKMC_OK;
+    }
+    DKMC_CUDA(cudaMemcpyAsync(prev, d_site_charge, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, ctx->stream));
+    inc.valid = true; inc.d_charge = d_site_charge; inc.d_out = d_out; inc.N = N;
+    inc.row_begin = row_begin; inc.row_end = row_end; inc.pbc = pbc;
+    inc.since_full = 0;
+    ++inc.full_sums;
     return DKMC_OK;
 }
 
@@ -609,8 +651,10 @@ int dkmc_poisson_gridless_begin(dkmc_ctx *ctx, int pbc, int N, const double *d_l
     DKMC_REQUIRE(!ctx->pw_pending.active, "a pairwise sum is already in flight: call dkmc_poisson_gridless_join");
     ChargedSite *src;
     int *src_idx, *total, *tile_counter;
-    int rc;
-    if ((rc = pairwise_prepare(ctx, N, d_x, d_y, d_z, d_site_charge, &src, &src_idx, &total, &tile_counter))) return rc;
+    int rc, accumulate;
+    const int *q_sum;
+    if ((rc = pairwise_incremental(ctx, pbc, N, d_site_charge, row_begin, row_end, d_site_potential_charge, &q_sum, &accumulate))) return rc;
+    if ((rc = pairwise_prepare(ctx, N, d_x, d_y, d_z, q_sum, &src, &src_idx, &total, &tile_counter))) return rc;
     PwCells cells;
     const bool use_cells = !pbc && ctx->pw_use_cells;
     if (use_cells && (rc = pairwise_bin_cells(ctx, N, d_x, d_y, d_z, d_sigma, src, src_idx, total, &cells))) return rc;
@@ -621,7 +665,7 @@ int dkmc_poisson_gridless_begin(dkmc_ctx *ctx, int pbc, int N, const double *d_l
     if (row_end > row_begin)
         if ((rc = pairwise_launch(ctx, ctx->side_stream, ctx->pw_side_blocks_per_sm, ctx->pw_side_threads, true, pbc, row_begin, row_end, d_lattice,
                                   d_sigma, d_k, d_x, d_y, d_z, src, src_idx, total, tile_counter,
-                                  d_site_potential_charge, use_cells ? &cells : nullptr))) return rc;
+                                  d_site_potential_charge, use_cells ? &cells : nullptr, accumulate))) return rc;
     DKMC_CUDA(cudaEventRecord(ctx->ev_pw1, ctx->side_stream));
     auto &pp = ctx->pw_pending;
     pp.active = true; pp.pbc = pbc; pp.N = N; pp.row_begin = row_begin; pp.row_end = row_end;
@@ -662,14 +706,16 @@ int dkmc_poisson_gridless_rows(dkmc_ctx *ctx, int pbc, int N, const double *d_la
     if (row_begin == row_end) return DKMC_OK;
     ChargedSite *src;
     int *src_idx, *total, *tile_counter;
-    int rc;
-    if ((rc = pairwise_prepare(ctx, N, d_x, d_y, d_z, d_site_charge, &src, &src_idx, &total, &tile_counter))) return rc;
+    int rc, accumulate;
+    const int *q_sum;
+    if ((rc = pairwise_incremental(ctx, pbc, N, d_site_charge, row_begin, row_end, d_site_potential_charge, &q_sum, &accumulate))) return rc;
+    if ((rc = pairwise_prepare(ctx, N, d_x, d_y, d_z, q_sum, &src, &src_idx, &total, &tile_counter))) return rc;
     PwCells cells;
     const bool use_cells = !pbc && ctx->pw_use_cells;
     if (use_cells && (rc = pairwise_bin_cells(ctx, N, d_x, d_y, d_z, d_sigma, src, src_idx, total, &cells))) return rc;
     if ((rc = pairwise_launch(ctx, ctx->stream, use_cells ? kPwCellFullBlocksPerSm : kPwFullBlocksPerSm, kPwThreads, false, pbc,
                               row_begin, row_end, d_lattice, d_sigma, d_k, d_x, d_y, d_z, src, src_idx, total, tile_counter,
-                              d_site_potential_charge, use_cells ? &cells : nullptr))) return rc;
+                              d_site_potential_charge, use_cells ? &cells : nullptr, accumulate))) return rc;
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
     return DKMC_OK;
 }
@@ -690,6 +736,21 @@ int dkmc_ctx_set_pairwise_cells(dkmc_ctx *ctx, int on) {
 int dkmc_ctx_set_pairwise_cutoff(dkmc_ctx *ctx, double cutoff_sigmas) {
     DKMC_REQUIRE(ctx != nullptr && cutoff_sigmas >= 0.0, "ctx / cutoff_sigmas >= 0");
     ctx->pw_cutoff_sigmas = cutoff_sigmas;
+    return DKMC_OK;
+}
+
+int dkmc_ctx_set_pairwise_incremental(dkmc_ctx *ctx, int refresh_every) {
+    DKMC_REQUIRE(ctx != nullptr && refresh_every >= 0, "ctx / refresh_every >= 0");
+    ctx->pw_inc.refresh_every = refresh_every;
+    ctx->pw_inc.valid = false;
+    ctx->pw_inc.since_full = 0;
+    return DKMC_OK;
+}
+
+int dkmc_pairwise_incremental_counts(dkmc_ctx *ctx, long long *full_sums, long long *delta_sums) {
+    DKMC_REQUIRE(ctx != nullptr && full_sums != nullptr && delta_sums != nullptr, "null pointer");
+    *full_sums = ctx->pw_inc.full_sums;
+    *delta_sums = ctx->pw_inc.delta_sums;
     return DKMC_OK;
 }
 

@@ -217,6 +217,16 @@ class Context:
         torch = _torch()
         check(self.lib.dkmc_ctx_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
+    def set_pairwise_incremental(self, refresh_every: int):
+        """opt-in: phi_c is updated by the charge differences since the previous step,
+        with a full sum every `refresh_every` steps; 0 switches it off"""
+        check(self.lib.dkmc_ctx_set_pairwise_incremental(self.h, int(refresh_every)))
+
+    def pairwise_incremental_counts(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        check(self.lib.dkmc_pairwise_incremental_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def launch_count(self) -> int:
         n = C.c_longlong(0)
         check(self.lib.dkmc_ctx_launch_count(self.h, C.byref(n)))

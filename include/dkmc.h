@@ -209,6 +209,17 @@ int dkmc_ctx_set_pairwise_cells(dkmc_ctx *ctx, int on);
  * it as a separate variant, never as the headline. */
 int dkmc_ctx_set_pairwise_cutoff(dkmc_ctx *ctx, double cutoff_sigmas);
 int dkmc_pairwise_pairs_evaluated(dkmc_ctx *ctx, long long *pairs);
+/* OPT-IN incremental update, default 0 = off.  Between two KMC steps only the sites
+ * touched by executed events change charge, so phi_c(new) = phi_c(old) + sum over the CHANGED sites of
+ * (q_new - q_old) * kernel: O(N * n_changed) instead of O(N * n_charged).  With refresh_every = R > 0
+ * a call on the same (d_site_charge, d_site_potential_charge, N, rows, pbc) as the previous one sums
+ * only the charge differences into d_site_potential_charge — which must still hold the previous
+ * result — and every R-th call is a full sum, bounding the rounding drift at ~R ulp of the largest
+ * entries (norm-wise; an entry whose sources all left keeps a residue of that size instead of its
+ * exact tiny value).  Like the cutoff this changes the WORK of a6: a bench variant, not the headline.
+ * dkmc_pairwise_incremental_counts: how many full / difference sums have run. */
+int dkmc_ctx_set_pairwise_incremental(dkmc_ctx *ctx, int refresh_every);
+int dkmc_pairwise_incremental_counts(dkmc_ctx *ctx, long long *full_sums, long long *delta_sums);
 /* share of each SM the overlapped pairwise kernel may occupy: CTAs per SM x threads per CTA */
 int dkmc_ctx_set_pairwise_share(dkmc_ctx *ctx, int blocks_per_sm, int threads_per_block);
 

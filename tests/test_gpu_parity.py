@@ -288,6 +288,52 @@ def test_poisson_gridless_no_charges(sim0, torch):
     assert float(buf.site_potential_charge.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("pbc", [0, 1])
+def test_poisson_gridless_incremental(base_case, O, torch, pbc):
+    """opt-in 8f-2: phi_c updated by the charge DIFFERENCES since the previous step (cell-list kernel
+    for pbc = 0, all-pairs kernel for pbc = 1), full sum every 4th call; against the oracle's full
+    sum after every step of a short trajectory"""
+    p, dev, sim, buf = make_sim(base_case, pbc=pbc)
+    nc = p.num_atoms_contact
+    dev.ctx.set_pairwise_incremental(4)
+    scale = None
+    for step in range(6):
+        dev.updateCharge(buf, p.metals)
+        dev.updatePotential(buf, p, 6.0, n_contact=nc)
+        got = buf.site_potential_charge.cpu().numpy()
+        q = buf.site_charge.cpu().numpy()
+        ref = O.poisson_gridless(dev.site_x, dev.site_y, dev.site_z, dev.lattice, pbc, q, p.sigma, p.k)
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() <= 1e-13 * scale, step
+        if step in (0, 4):
+            assert elementwise_rel(got, ref) <= TOL          # a full sum: element-wise as in the default mode
+        sim.executeKMCStep(buf, dev)
+    assert dev.ctx.pairwise_incremental_counts() == (2, 4)
+    # a different output array, or switching the mode off and on, falls back to a full sum
+    dev.ctx.set_pairwise_incremental(0)
+    dev.updateCharge(buf, p.metals)
+    dev.updatePotential(buf, p, 6.0, n_contact=nc)
+    assert dev.ctx.pairwise_incremental_counts() == (2, 4)
+
+
+def test_trajectory_with_incremental_pairwise(base_case, torch):
+    """the 6 V golden trajectory of the reference run, event for event, with phi_c carried
+    incrementally from step to step (full sum every 3rd step)"""
+    import hashlib
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "s_traj_6V.npz"))
+    p, dev, sim, buf = make_sim(base_case)
+    dev.ctx.set_pairwise_incremental(3)
+    for s, Vd in enumerate(g["Vd"]):
+        dev.updateCharge(buf, p.metals)
+        assert dev.updatePotential(buf, p, float(Vd), n_contact=p.num_atoms_contact)["cg_converged"]
+        t = sim.executeKMCStep(buf, dev, record_events=65536)
+        assert np.array_equal(sim.last_events[:, 1:3], g["ev_ij"][g["ev_ptr"][s]:g["ev_ptr"][s + 1]]), f"step {s}"
+        assert abs(t - g["step_time"][s]) <= 1e-7 * abs(g["step_time"][s]), f"step {s}"
+        assert hashlib.sha256(buf.site_element.cpu().numpy().tobytes()).hexdigest() == str(g["el_sha"][s])
+    assert dev.ctx.pairwise_incremental_counts() == (2, 4)
+
+
 # ------------------------------------------------------------------ a7 rate table
 def _load_golden_state(sim0, golden_step0, torch):
     p, dev, sim, buf = sim0
