@@ -4,9 +4,9 @@
 reference's host classes; the compute lives in lib/libdkmc_b200.so (include/dkmc.h).
 """
 from .host import (DEFAULT_LAYERS, Context, Device, GPUBuffers, KMCParameters, KMCProcess, Layer,
-                   RandomNumberGenerator, read_xyz, write_xyz)
+                   RandomNumberGenerator, Snapshot, read_xyz, write_snapshot, write_xyz)
 from ._capi import DkmcError, SolverOpts, SolveInfo, StepInfo, Sparsity
 
 __all__ = ["DEFAULT_LAYERS", "Context", "Device", "GPUBuffers", "KMCParameters", "KMCProcess", "Layer",
-           "RandomNumberGenerator", "read_xyz", "write_xyz", "DkmcError", "SolverOpts", "SolveInfo",
+           "RandomNumberGenerator", "Snapshot", "read_xyz", "write_snapshot", "write_xyz", "DkmcError", "SolverOpts", "SolveInfo",
            "StepInfo", "Sparsity"]

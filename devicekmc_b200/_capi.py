@@ -62,7 +62,7 @@ class StepInfo(C.Structure):
 EXPORTS = [
     "dkmc_version", "dkmc_last_error", "dkmc_get_gpu_info", "dkmc_set_gpu", "dkmc_device_count",
     "dkmc_ctx_create", "dkmc_ctx_destroy", "dkmc_ctx_set_stream", "dkmc_ctx_synchronize",
-    "dkmc_ctx_launch_count", "dkmc_set_layer_energies", "dkmc_neighbor_count", "dkmc_neighbor_fill", "dkmc_neighbor_table_host",
+    "dkmc_ctx_launch_count", "dkmc_set_layer_energies", "dkmc_neighbor_count", "dkmc_neighbor_fill", "dkmc_neighbor_table_host", "dkmc_snapshot_begin", "dkmc_snapshot_ready", "dkmc_snapshot_wait",
     "dkmc_initialize_sparsity", "dkmc_free_sparsity", "dkmc_update_charge", "dkmc_default_solver_opts",
     "dkmc_background_potential_sparse", "dkmc_update_CB_edge_sparse", "dkmc_assemble_K", "dkmc_spmv", "dkmc_spmv_window", "dkmc_ctx_set_window_spmv", "dkmc_ctx_set_packed_spmv", "dkmc_solve_cg",
     "dkmc_poisson_gridless", "dkmc_poisson_gridless_rows", "dkmc_poisson_gridless_begin",
@@ -96,6 +96,9 @@ def load() -> C.CDLL:
         lib.dkmc_set_layer_energies.argtypes = [vp, ci, vp, vp, vp, vp]
         lib.dkmc_neighbor_count.argtypes = [vp, ci, vp, vp, vp, vp, ci, cd, C.POINTER(ci)]
         lib.dkmc_neighbor_fill.argtypes = [vp, ci, vp, vp, vp, vp, ci, cd, ci, vp]
+        lib.dkmc_snapshot_begin.argtypes = [vp, ci] + [vp] * 9
+        lib.dkmc_snapshot_ready.argtypes = [vp, C.POINTER(ci)]
+        lib.dkmc_snapshot_wait.argtypes = [vp]
         lib.dkmc_neighbor_table_host.argtypes = [vp, ci, vp, vp, vp, vp, ci, cd, C.POINTER(ci), vp]
         lib.dkmc_initialize_sparsity.argtypes = [vp, ci, ci, vp, ci, ci, C.POINTER(Sparsity)]
         lib.dkmc_free_sparsity.argtypes = [vp, C.POINTER(Sparsity)]

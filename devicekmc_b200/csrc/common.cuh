@@ -16,7 +16,7 @@ namespace dkmc {
 
 constexpr int kWarp = 32;
 constexpr int kMaxLayers = 16;
-constexpr int kNumSlots = 48;
+constexpr int kNumSlots = 64;
 constexpr int kMaxLevels = 8;
 
 void set_error(const char *fmt, ...);
@@ -52,7 +52,7 @@ enum Slot : int {
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
     S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_PCOL, S_CG_PDIAG, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
-    S_NB_HOSTPOS, S_NB_HOSTTAB, S_PW_PREVQ, S_PW_DQ,
+    S_NB_HOSTPOS, S_NB_HOSTTAB, S_PW_PREVQ, S_PW_DQ, S_SNAP_STAGE,
     S_LAST
 };
 static_assert(S_LAST <= kNumSlots, "increase kNumSlots");
@@ -148,6 +148,10 @@ struct dkmc_ctx {
         const int *d_charge = nullptr; const double *d_out = nullptr; int N = 0, row_begin = 0, row_end = 0, pbc = 0;
         long long full_sums = 0, delta_sums = 0;
     } pw_inc;
+    // snapshot copies: staged on `stream`, moved to the host on `io_stream`
+    cudaStream_t io_stream = nullptr;
+    cudaEvent_t ev_snap_staged = nullptr, ev_snap_done = nullptr;
+    bool snap_pending = false;
     int pw_side_threads = 128;
     int pw_side_blocks_per_sm = 3;   // residency of the pairwise kernel while it shares the SMs with the CG
 };

@@ -46,6 +46,19 @@ int ensure_slot(dkmc_ctx *ctx, int slot, size_t bytes, void **out) {
     return DKMC_OK;
 }
 
+// fused staging pass of dkmc_snapshot_begin: one coalesced read of the five site arrays
+__global__ void __launch_bounds__(256) snapshot_stage_kernel(
+    int N, const int *__restrict__ element, const int *__restrict__ charge, const double *__restrict__ pb,
+    const double *__restrict__ pc, const double *__restrict__ power, int *__restrict__ s_el, int *__restrict__ s_q,
+    double *__restrict__ s_pot, double *__restrict__ s_pow) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    s_el[i] = element[i];
+    s_q[i] = charge[i];
+    s_pot[i] = __dadd_rn(pb[i], pc[i]);   // Device.cpp:250: site_potential_boundary[i] + site_potential_charge[i]
+    if (power != nullptr) s_pow[i] = power[i];
+}
+
 }  // namespace dkmc
 
 using namespace dkmc;
@@ -101,6 +114,9 @@ int dkmc_ctx_create(dkmc_ctx **out) {
     DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     DKMC_CUDA(cudaEventCreate(&ctx->ev_pw0));
     DKMC_CUDA(cudaEventCreate(&ctx->ev_pw1));
+    DKMC_CUDA(cudaStreamCreateWithFlags(&ctx->io_stream, cudaStreamNonBlocking));
+    DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap_staged, cudaEventDisableTiming));
+    DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap_done, cudaEventDisableTiming));
     if (const char *e = getenv("DKMC_PACKED_SPMV")) ctx->use_packed_spmv = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DKMC_WINDOW_SPMV")) ctx->use_window_spmv = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DKMC_PW_SIDE_BPS")) { int v = atoi(e); if (v > 0) ctx->pw_side_blocks_per_sm = v; }
@@ -112,6 +128,9 @@ int dkmc_ctx_destroy(dkmc_ctx *ctx) {
     if (!ctx) return DKMC_OK;
     cudaStreamSynchronize(ctx->stream);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->io_stream) { cudaStreamSynchronize(ctx->io_stream); cudaStreamDestroy(ctx->io_stream); }
+    if (ctx->ev_snap_staged) cudaEventDestroy(ctx->ev_snap_staged);
+    if (ctx->ev_snap_done) cudaEventDestroy(ctx->ev_snap_done);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_pw0) cudaEventDestroy(ctx->ev_pw0);
     if (ctx->ev_pw1) cudaEventDestroy(ctx->ev_pw1);
@@ -124,6 +143,58 @@ int dkmc_ctx_destroy(dkmc_ctx *ctx) {
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->ev_c) cudaEventDestroy(ctx->ev_c);
     delete ctx;
+    return DKMC_OK;
+}
+
+// ---------------------------------------------------------------- snapshot
+// What Device::writeSnapshot prints per site (Device.cpp:236-252) besides the static positions:
+// element, potential_boundary + potential_charge (one rounded add, as on the host), power; the charge
+// goes along for restarts.  One fused pass stages them (40 B read, 24 B written per site); the event
+// loop may then mutate the live arrays while the staged copy drains to the host on its own stream.
+int dkmc_snapshot_begin(dkmc_ctx *ctx, int N, const int *d_site_element, const int *d_site_charge,
+                        const double *d_site_potential_boundary, const double *d_site_potential_charge,
+                        const double *d_site_power, int *h_element, int *h_charge, double *h_potential,
+                        double *h_power) {
+    DKMC_REQUIRE(ctx && d_site_element && d_site_charge && d_site_potential_boundary && d_site_potential_charge &&
+                 h_element && h_charge && h_potential, "null pointer");
+    DKMC_REQUIRE(N > 0, "N must be positive");
+    DKMC_REQUIRE((d_site_power == nullptr) == (h_power == nullptr), "d_site_power and h_power go together");
+    DKMC_REQUIRE(!ctx->snap_pending, "a snapshot is already in flight: call dkmc_snapshot_wait");
+    double *stage;
+    int rc;
+    if ((rc = ensure<double>(ctx, S_SNAP_STAGE, (size_t)3 * N + 2, &stage))) return rc;
+    double *s_pot = stage, *s_pow = stage + N;
+    int *s_el = reinterpret_cast<int *>(stage + 2 * (size_t)N), *s_q = s_el + N;
+    DKMC_LAUNCH(ctx, snapshot_stage_kernel, ceil_div(N, 256), 256, 0, N, d_site_element, d_site_charge,
+                d_site_potential_boundary, d_site_potential_charge, d_site_power, s_el, s_q, s_pot, s_pow);
+    DKMC_CUDA(cudaEventRecord(ctx->ev_snap_staged, ctx->stream));
+    DKMC_CUDA(cudaStreamWaitEvent(ctx->io_stream, ctx->ev_snap_staged, 0));
+    DKMC_CUDA(cudaMemcpyAsync(h_element, s_el, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, ctx->io_stream));
+    DKMC_CUDA(cudaMemcpyAsync(h_charge, s_q, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, ctx->io_stream));
+    DKMC_CUDA(cudaMemcpyAsync(h_potential, s_pot, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->io_stream));
+    if (h_power) DKMC_CUDA(cudaMemcpyAsync(h_power, s_pow, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->io_stream));
+    DKMC_CUDA(cudaEventRecord(ctx->ev_snap_done, ctx->io_stream));
+    // `stream` does NOT wait for the drain; the staging buffer is protected by snap_pending (a second
+    // begin is refused until dkmc_snapshot_wait has seen ev_snap_done)
+    ctx->snap_pending = true;
+    return DKMC_OK;
+}
+
+int dkmc_snapshot_ready(dkmc_ctx *ctx, int *ready) {
+    DKMC_REQUIRE(ctx && ready, "null pointer");
+    *ready = 1;
+    if (!ctx->snap_pending) return DKMC_OK;
+    cudaError_t e = cudaEventQuery(ctx->ev_snap_done);
+    if (e == cudaErrorNotReady) { *ready = 0; return DKMC_OK; }
+    DKMC_CUDA(e);
+    return DKMC_OK;
+}
+
+int dkmc_snapshot_wait(dkmc_ctx *ctx) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    if (!ctx->snap_pending) return DKMC_OK;
+    DKMC_CUDA(cudaEventSynchronize(ctx->ev_snap_done));
+    ctx->snap_pending = false;
     return DKMC_OK;
 }
 

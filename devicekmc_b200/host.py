@@ -73,6 +73,22 @@ def write_xyz(filename: str, element, x, y, z, extra=None):
             f.write(f"{return_element(element[i])}   {float(x[i])!r}   {float(y[i])!r}   {float(z[i])!r}{tail}\n")
 
 
+def write_snapshot(path: str, element, x, y, z, potential, power=None):
+    """The file Device::writeSnapshot produces (Device.cpp:236-252): `element x y z potential power`,
+    three blanks between columns, default ostream formatting (= %g, 6 significant digits)."""
+    names = [return_element(e) for e in range(NULL_ELEMENT + 1)]
+    n = len(x)
+    pw = np.zeros(n) if power is None else power
+    with open(path, "w") as f:
+        f.write(f"{n}\n\n")
+        for lo in range(0, n, 65536):
+            hi = min(n, lo + 65536)
+            f.write("".join(
+                f"{names[e]}   {a:g}   {b:g}   {c:g}   {v:g}   {w:g}\n"
+                for e, a, b, c, v, w in zip(element[lo:hi].tolist(), x[lo:hi].tolist(), y[lo:hi].tolist(),
+                                            z[lo:hi].tolist(), potential[lo:hi].tolist(), pw[lo:hi].tolist())))
+
+
 class RandomNumberGenerator:
     """std::mt19937 + std::uniform_real_distribution<double>(0,1) as libstdc++ implements it
     (generate_canonical<double,53>: two 32-bit draws per double).  random_num.h:4-23."""
@@ -355,6 +371,13 @@ class Device:
                 "overlap": bool(overlap)}
 
 
+    def writeSnapshot(self, filename: str, foldername: str):
+        """Device.cpp:236-252, from the host arrays (call sync_GPUToHost first, as kmc_main.cpp:196-201
+        does, or use GPUBuffers.snapshot_begin for a copy that does not stall the step)"""
+        import os
+        write_snapshot(os.path.join(".", foldername, filename), self.site_element, self.site_x, self.site_y, self.site_z,
+                       self.site_potential_boundary + self.site_potential_charge, getattr(self, "site_power", None))
+
     def _set_laplace(self, gpubuf, p, Vd, opts=None):
         lib = self.ctx.lib
         nc = p.num_atoms_first_layer                      # potential_solver.cpp:7-8
@@ -456,6 +479,22 @@ class GPUBuffers:
             self._pinned(device, name).copy_(getattr(self, name), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    def snapshot_begin(self, device: Device) -> "Snapshot":
+        """stage element / charge / potential on the device and start draining them into
+        page-locked host buffers on the copy stream; returns at once.  The step may go on (and the event
+        loop may mutate the site state) while the snapshot drains; Snapshot.write() produces the file
+        Device::writeSnapshot would have written at this point."""
+        torch = _torch()
+        if "snap" not in self._pin:
+            self._pin["snap"] = (torch.empty(self.N_, dtype=torch.int32).pin_memory(),
+                                 torch.empty(self.N_, dtype=torch.int32).pin_memory(),
+                                 torch.empty(self.N_, dtype=torch.float64).pin_memory())
+        el, q, pot = self._pin["snap"]
+        check(self.ctx.lib.dkmc_snapshot_begin(self.ctx.h, self.N_, _ptr(self.site_element), _ptr(self.site_charge),
+                                               _ptr(self.site_potential_boundary), _ptr(self.site_potential_charge), None,
+                                               _ptr(el), _ptr(q), _ptr(pot), None))
+        return Snapshot(self.ctx, device, el, q, pot)
+
     def h2d_bytes(self) -> int:
         return self.N_ * (4 + 4 + 8 + 8 + 8)
 
@@ -465,6 +504,38 @@ class GPUBuffers:
         for sp in self._sparsity.values():
             self.ctx.lib.dkmc_free_sparsity(self.ctx.h, C.byref(sp))
         self._sparsity.clear()
+
+
+class Snapshot:
+    """A snapshot in flight (GPUBuffers.snapshot_begin)."""
+
+    def __init__(self, ctx: Context, device: Device, el, q, pot):
+        self.ctx, self._dev, self._el, self._q, self._pot = ctx, device, el, q, pot
+        self._thread = None
+
+    def ready(self) -> bool:
+        r = C.c_int(0)
+        check(self.ctx.lib.dkmc_snapshot_ready(self.ctx.h, C.byref(r)))
+        return bool(r.value)
+
+    def wait(self):
+        """blocks until the copies are complete; returns (element, charge, potential) host arrays
+        (views of the staging buffers: valid until the next snapshot_begin)"""
+        check(self.ctx.lib.dkmc_snapshot_wait(self.ctx.h))
+        return self._el.numpy(), self._q.numpy(), self._pot.numpy()
+
+    def write(self, filename: str, foldername: str = "."):
+        import os
+        el, q, pot = self.wait()
+        d = self._dev
+        write_snapshot(os.path.join(".", foldername, filename), el, d.site_x, d.site_y, d.site_z, pot)
+
+    def write_async(self, filename: str, foldername: str = "."):
+        """formats and writes the file on a host thread (the ctypes calls of the step release the GIL)"""
+        import threading
+        self._thread = threading.Thread(target=self.write, args=(filename, foldername), daemon=True)
+        self._thread.start()
+        return self._thread
 
 
 class KMCProcess:

@@ -314,6 +314,22 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
  * pairwise sum, which MEASURED_PEAKS.json does not carry. */
 int dkmc_probe_fp64_tflops(dkmc_ctx *ctx, double *tflops);
 
+/* ---- snapshots that do not stall the step.  Device::writeSnapshot (Device.cpp:236-252)
+ * prints per site: element, position, potential_boundary + potential_charge, power — after a blocking
+ * sync_GPUToHost of all seven site arrays (kmc_main.cpp:196-201, gpu_buffers.cpp:39-55).  begin: one
+ * fused pass on the context's stream stages element, charge, the summed potential and (if given) the
+ * power; a separate copy stream then moves the staged arrays into the caller's HOST buffers (page-
+ * locked memory makes the copies truly asynchronous) while the caller goes on — the event loop may
+ * mutate site_element / site_charge right away.  wait: blocks until the host buffers are complete;
+ * ready: non-blocking query.  One snapshot in flight per context.  d_site_power / h_power may both be
+ * NULL.  Multi-GPU: the site state is replicated, so rank 0 alone snapshots. */
+int dkmc_snapshot_begin(dkmc_ctx *ctx, int N, const int *d_site_element, const int *d_site_charge,
+                        const double *d_site_potential_boundary, const double *d_site_potential_charge,
+                        const double *d_site_power, int *h_element, int *h_charge, double *h_potential,
+                        double *h_power);
+int dkmc_snapshot_ready(dkmc_ctx *ctx, int *ready);
+int dkmc_snapshot_wait(dkmc_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,6 +177,12 @@ void ref_get_cb_edge(void *h, double *out) {
     std::memcpy(out, s->dev->site_CB_edge.data(), s->dev->N * sizeof(double));
 }
 
+// Device::writeSnapshot (Device.cpp:236-252): writes ./<folder>/<filename>
+void ref_write_snapshot(void *h, const char *filename, const char *folder) {
+    auto *s = static_cast<RefSim *>(h);
+    s->dev->writeSnapshot(filename, folder);
+}
+
 // Device::poisson_gridless (potential_solver.cpp:412-432)
 void ref_poisson_gridless(void *h) {
     auto *s = static_cast<RefSim *>(h);

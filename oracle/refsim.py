@@ -137,6 +137,11 @@ class RefSim:
         self._lib.ref_laplace_cb_edge(self._h, float(Vd))
         return self._get("ref_get_cb_edge", self.N, np.float64)
 
+    def write_snapshot(self, filename: str, folder: str):
+        """Device::writeSnapshot: writes ./<folder>/<filename> relative to the current directory"""
+        self._lib.ref_write_snapshot.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        self._lib.ref_write_snapshot(self._h, filename.encode(), folder.encode())
+
     def poisson_gridless(self):
         self._lib.ref_poisson_gridless(self._h)
 

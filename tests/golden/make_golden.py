@@ -11,6 +11,8 @@ rnd_seed_kmc = 1, CPU build, 1 process):
   s_traj_ramp.npz  the kmc_main.cpp:136-279 loop on the shipped V_switch ramp, first 12 KMC steps:
                    per step Vd, executed (i, j) pairs, step time, sha256 of site_element/charge
   s_traj_6V.npz    the same loop at constant Vd = 6 V, 6 KMC steps (many events per step)
+  s_snapshot.npz   Device::writeSnapshot (Device.cpp:236-252) of the s_step0 state: sha256 and size of the
+                   file, its first and last lines
   s_cb_edge.npz    Device::setLaplacePotential (CPU branch, potential_solver.cpp:4-139) at Vd = 1.5 V:
                    site_CB_edge of all sites
 """
@@ -62,6 +64,29 @@ def step0():
     print("step0 written", len(nz), "events")
 
 
+def snapshot():
+    import tempfile
+    s = new_sim()
+    s.update_charge()
+    s.background_potential(1.5)
+    s.poisson_gridless()
+    g = np.load(os.path.join(OUT, "s_step0.npz"))
+    assert np.array_equal(s.potential_boundary(), g["potential_boundary"]) and np.array_equal(s.potential_charge(), g["potential_charge"])
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            os.mkdir("Results")
+            s.write_snapshot("snapshot_0.xyz", "Results")
+            raw = open(os.path.join(d, "Results", "snapshot_0.xyz"), "rb").read()
+        finally:
+            os.chdir(cwd)
+    lines = raw.decode().split("\n")
+    np.savez_compressed(os.path.join(OUT, "s_snapshot.npz"), sha256=hashlib.sha256(raw).hexdigest(), size=len(raw),
+                        head=np.array(lines[:6]), tail=np.array(lines[-4:]), sample=np.array(lines[2 + 3000:2 + 3006]))
+    print("snapshot written", len(raw), "bytes;", lines[2], "|", lines[3002])
+
+
 def cb_edge():
     s = new_sim()
     Vd = 1.5
@@ -102,9 +127,11 @@ def trajectory(name, schedule, nsteps):
 if __name__ == "__main__":
     import devicekmc_b200.host as H
     p = H.KMCParameters.from_file(REF + "parameters.txt")
-    which = sys.argv[1:] or ["step0", "ramp", "6V", "cb_edge"]
+    which = sys.argv[1:] or ["step0", "ramp", "6V", "cb_edge", "snapshot"]
     if "step0" in which:
         step0()
+    if "snapshot" in which:
+        snapshot()
     if "cb_edge" in which:
         cb_edge()
     if "ramp" in which:

@@ -194,6 +194,22 @@ def test_parameters_parser_and_layers():
     assert len(p.V_switch) == len(p.t_switch) == 3 and p.V_switch[1] == 0.0240480961923848
 
 
+def test_snapshot_file_matches_reference_writer(base_case, golden_step0, tmp_path):
+    """SURVEY 8f-4: the snapshot writer against the file Device::writeSnapshot (Device.cpp:236-252)
+    of the reference build wrote for the s_step0 state — byte for byte"""
+    from devicekmc_b200.host import write_snapshot
+    g = np.load(os.path.join(GOLDEN, "s_snapshot.npz"))
+    path = tmp_path / "snapshot_0.xyz"
+    write_snapshot(str(path), base_case["element"], base_case["x"], base_case["y"], base_case["z"],
+                   golden_step0["potential_boundary"] + golden_step0["potential_charge"])
+    raw = path.read_bytes()
+    lines = raw.decode().split("\n")
+    assert lines[:6] == g["head"].tolist() and lines[-4:] == g["tail"].tolist()
+    assert lines[3002:3008] == g["sample"].tolist()
+    assert len(raw) == int(g["size"])
+    assert hashlib.sha256(raw).hexdigest() == str(g["sha256"])
+
+
 def test_tiled_device_structure(O):
     from devicekmc_b200 import structures as S
     el, x, y, z, lat, nc = S.tile_device(2, 2)

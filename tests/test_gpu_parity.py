@@ -484,6 +484,35 @@ def test_trajectory_matches_reference(base_case, torch, name):
     assert np.array_equal(buf.site_element.cpu().numpy(), g["element_last"].astype(np.int32))
 
 
+# ------------------------------------------------------------------ 8f-4 snapshots that do not stall the step
+def test_snapshot_is_a_consistent_copy_while_the_step_goes_on(base_case, golden_step0, torch, tmp_path):
+    import hashlib
+    from conftest import GOLDEN
+    sim1 = make_sim(base_case)
+    p, dev, sim, buf = sim1
+    _load_golden_state(sim1, golden_step0, torch)
+    snap = buf.snapshot_begin(dev)
+    # the state is mutated right away: events on the live arrays, a new potential
+    sim.executeKMCStep(buf, dev)
+    buf.site_potential_boundary.add_(1.0)
+    buf.site_charge.zero_()
+    with pytest.raises(Exception):
+        buf.snapshot_begin(dev)                       # one snapshot in flight per context
+    el, q, pot = snap.wait()
+    assert np.array_equal(el, golden_step0["element"].astype(np.int32))
+    assert np.array_equal(q, golden_step0["charge"].astype(np.int32))
+    assert np.array_equal(pot, golden_step0["potential_boundary"] + golden_step0["potential_charge"])
+    assert not np.array_equal(buf.site_element.cpu().numpy(), el)      # the live state did move on
+    # the file is the one the reference's Device::writeSnapshot wrote for this state
+    snap.write("snapshot_0.xyz", str(tmp_path))
+    g = np.load(os.path.join(GOLDEN, "s_snapshot.npz"))
+    assert hashlib.sha256((tmp_path / "snapshot_0.xyz").read_bytes()).hexdigest() == str(g["sha256"])
+    # and a second snapshot works once the first has been waited for
+    snap2 = buf.snapshot_begin(dev)
+    el2, q2, _ = snap2.wait()
+    assert np.array_equal(el2, buf.site_element.cpu().numpy()) and not q2.any()
+
+
 # ------------------------------------------------------------------ window-staged SpMV + stream overlap
 @pytest.fixture(scope="module")
 def cell_sim():
