@@ -52,7 +52,7 @@ enum Slot : int {
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
     S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_PCOL, S_CG_PDIAG, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
-    S_NB_HOSTPOS, S_NB_HOSTTAB, S_PW_PREVQ, S_PW_DQ, S_SNAP_STAGE,
+    S_NB_HOSTPOS, S_NB_HOSTTAB, S_PW_PREVQ, S_PW_DQ, S_SNAP_STAGE, S_EV_NZROWS, S_EV_BATCHSUM,
     S_LAST
 };
 static_assert(S_LAST <= kNumSlots, "increase kNumSlots");

@@ -192,6 +192,8 @@ struct LoopArgs {
     const int *hist;
     EvState *state;
     int exact_mode;        // 1 = always replay exactly (test hook)
+    int *nz_rows;          // scratch of select_exact: N ints
+    double *batch_sum;     // scratch of select_exact: one running sum per batch of 32 row segments
 };
 
 __device__ __forceinline__ double ldv(const double *p) { return __ldcg(p); }
@@ -264,36 +266,103 @@ __device__ void select_walk(const LoopArgs &a, double u, const double *errA, con
     idx_out = idx_sel; psum_out = psum; flag_out = flag; delta_out = delta;
 }
 
-// exact replay of utils.h:91-99 + std::upper_bound by one thread (rare path)
+// Exact replay of utils.h:91-99 + std::upper_bound (rare path): the strictly left-to-right sum of
+// the current rates.  Adding a zero changes nothing (x + 0.0 == x, and 0.0 + p == p), so only the
+// non-zero entries have to be added, in table order.  The whole CTA cooperates, one thread adds:
+//   A. ordered compaction of the rows whose row sum is not 0 (rates are >= 0: the sum is 0 iff every
+//      entry is) into nz_rows — one coalesced pass over the N row sums;
+//   B. items = (non-zero row, segment of 32 slots), one per warp and batch: the warp compacts the
+//      non-zero entries of its segment into shared memory in slot order; thread 0 adds the batch
+//      sequentially and records the running sum after each batch;
+//   C. Psum = the last running sum; the first batch whose running sum exceeds u * Psum is replayed
+//      from its starting value to find the entry.
+// Cost: O(N / threads) + O(non-zero rows) instead of one thread walking all N rows twice (9 s per
+// call at 4 M sites).  Must be called by ALL threads of the CTA; every thread returns the same result.
 __device__ void select_exact(const LoopArgs &a, double u, int &idx_out, double &psum_out) {
+    constexpr int kWarps = kLoopThreads / 32;
+    static_assert(kWarps == 32, "the warp-count scan below maps one warp of the CTA to one lane");
+    __shared__ int s_wcnt[2][kWarps];
+    __shared__ double s_val[kWarps][32];
+    __shared__ unsigned char s_slot[kWarps][32];
+    __shared__ int s_cnt[kWarps], s_row[kWarps];
+    __shared__ double s_acc;
+    __shared__ int s_found, s_first_batch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *rowsum = a.levels + a.lv.off[0];
-    double acc = 0.0;
-    bool first = true;
-    for (int r = 0; r < a.N; ++r) {
-        if (ldv(rowsum + r) == 0.0) continue;
-        const double *row = a.ev_prob + (size_t)r * a.nn;
-        for (int s = 0; s < a.nn; ++s) {
-            double p = ldv(row + s);
-            if (p != 0.0) { acc = first ? p : acc + p; first = false; }
-        }
+    // ---- A
+    int total = 0, buf = 0;
+    for (int base = 0; base < a.N; base += kLoopThreads, buf ^= 1) {
+        const int r = base + tid;
+        const bool nz = r < a.N && ldv(rowsum + r) != 0.0;
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) s_wcnt[buf][warp] = __popc(m);
+        __syncthreads();
+        const int c = s_wcnt[buf][lane];
+        const int inc = warp_inclusive_scan_int(c, lane);
+        const int woff = __shfl_sync(0xffffffffu, inc - c, warp);
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (nz) a.nz_rows[total + woff + __popc(m & ((1u << lane) - 1u))] = r;
+        total += tot;
     }
-    psum_out = acc;
-    const double number = u * acc;
-    idx_out = -1;
-    acc = 0.0;
-    first = true;
-    for (int r = 0; r < a.N; ++r) {
-        if (ldv(rowsum + r) == 0.0) continue;
-        const double *row = a.ev_prob + (size_t)r * a.nn;
-        for (int s = 0; s < a.nn; ++s) {
-            double p = ldv(row + s);
-            if (p != 0.0) {
-                acc = first ? p : acc + p;
-                first = false;
-                if (acc > number) { idx_out = r * a.nn + s; return; }
+    __syncthreads();   // nz_rows is read below by other threads than its writers
+    const int nseg = (a.nn + 31) / 32;
+    const long long n_items = (long long)total * nseg;
+    const int n_batches = (int)((n_items + kWarps - 1) / kWarps);
+    // one batch: every warp stages its item; returns after the staging barrier
+    auto stage = [&](int batch) {
+        const long long item = (long long)batch * kWarps + warp;
+        int cnt = 0, row = -1;
+        if (item < n_items) {
+            row = a.nz_rows[item / nseg];
+            const int slot = (int)(item % nseg) * 32 + lane;
+            const double v = slot < a.nn ? ldv(a.ev_prob + (size_t)row * a.nn + slot) : 0.0;
+            const unsigned m = __ballot_sync(0xffffffffu, v != 0.0);
+            if (v != 0.0) {
+                const int pos = __popc(m & ((1u << lane) - 1u));
+                s_val[warp][pos] = v;
+                s_slot[warp][pos] = (unsigned char)slot;
             }
+            cnt = __popc(m);
         }
+        if (lane == 0) { s_cnt[warp] = cnt; s_row[warp] = row; }
+        __syncthreads();
+    };
+    // ---- B
+    if (tid == 0) { s_acc = 0.0; s_found = -1; s_first_batch = n_batches; }
+    for (int batch = 0; batch < n_batches; ++batch) {
+        stage(batch);
+        if (tid == 0) {
+            double acc = s_acc;
+            for (int w = 0; w < kWarps; ++w)
+                for (int k = 0; k < s_cnt[w]; ++k) acc = acc + s_val[w][k];
+            s_acc = acc;
+            a.batch_sum[batch] = acc;
+        }
+        __syncthreads();
     }
+    __syncthreads();
+    const double psum = s_acc;
+    const double number = u * psum;
+    // ---- C: first batch whose running sum exceeds the target (running sums never decrease)
+    for (int b0 = tid; b0 < n_batches; b0 += kLoopThreads)
+        if (a.batch_sum[b0] > number) atomicMin(&s_first_batch, b0);
+    __syncthreads();
+    const int fb = s_first_batch;
+    if (fb < n_batches) {
+        stage(fb);
+        if (tid == 0) {
+            double acc = fb > 0 ? a.batch_sum[fb - 1] : 0.0;
+            for (int w = 0; w < kWarps && s_found < 0; ++w)
+                for (int k = 0; k < s_cnt[w]; ++k) {
+                    acc = acc + s_val[w][k];
+                    if (acc > number) { s_found = s_row[w] * a.nn + (int)s_slot[w][k]; break; }
+                }
+        }
+        __syncthreads();
+    }
+    idx_out = s_found;
+    psum_out = psum;
+    __syncthreads();   // the shared scratch may be reused by the next call
 }
 
 __global__ void __launch_bounds__(kLoopThreads, 1) event_loop_kernel(LoopArgs a) {
@@ -358,13 +427,11 @@ __global__ void __launch_bounds__(kLoopThreads, 1) event_loop_kernel(LoopArgs a)
             if (lane == 0) { s_idx = idx; s_flag = flag; s_psum = psum; s_delta = delta; }
         }
         __syncthreads();
-        if (s_flag == 2) {
-            if (tid == 0) {
-                int idx;
-                double psum;
-                select_exact(a, u1, idx, psum);
-                s_idx = idx; s_psum = psum; s_flag = idx >= 0 ? 0 : 1; s_nfb += 1;
-            }
+        if (s_flag == 2) {   // uniform: s_flag is shared
+            int idx;
+            double psum;
+            select_exact(a, u1, idx, psum);
+            if (tid == 0) { s_idx = idx; s_psum = psum; s_flag = idx >= 0 ? 0 : 1; s_nfb += 1; }
             __syncthreads();
         }
         const int idx = s_flag == 0 ? s_idx : -1;
@@ -542,6 +609,11 @@ static int run_loop(dkmc_ctx *ctx, const double *uniforms, int n_uniforms, int *
     a.events_out = events_out ? d_events : nullptr;
     a.max_events = max_events; a.events_base = 0;
     a.hist = static_cast<int *>(ctx->slot_ptr[S_EV_SCRATCH]);
+    {
+        const size_t items = (size_t)ev.N * (size_t)((ev.nn + 31) / 32);
+        if ((rc = ensure<int>(ctx, S_EV_NZROWS, (size_t)ev.N, &a.nz_rows))) return rc;
+        if ((rc = ensure<double>(ctx, S_EV_BATCHSUM, items / (kLoopThreads / 32) + 2, &a.batch_sum))) return rc;
+    }
     a.state = d_state;
     a.exact_mode = ctx->exact_select;
     DKMC_LAUNCH(ctx, event_loop_kernel, 1, kLoopThreads, 0, a);

@@ -32,6 +32,24 @@ def big():
     return dict(p=p, dev=dev, sim=sim, buf=buf, nc=nc, nb=dev.neigh_idx.reshape(dev.N, -1))
 
 
+def _charges(big):
+    """site charges of the initial structure (device run), computed once"""
+    if "q" not in big:
+        big["dev"].updateCharge(big["buf"], big["p"].metals)
+        big["q"] = big["buf"].site_charge.cpu().numpy()
+    return big["q"]
+
+
+def _potentials(big):
+    """the 10 V state: phi_b and phi_c of the initial structure (device run), computed once"""
+    if "pb" not in big:
+        _charges(big)
+        assert big["dev"].updatePotential(big["buf"], big["p"], 10.0, n_contact=big["nc"])["cg_converged"]
+        big["pb"] = big["buf"].site_potential_boundary.cpu().numpy()
+        big["pc"] = big["buf"].site_potential_charge.cpu().numpy()
+    return big["pb"], big["pc"]
+
+
 def test_fullsize_graph_charge_and_csr_bit_exact(big, O):
     p, dev, buf, nc = big["p"], big["dev"], big["buf"], big["nc"]
     assert dev.N == 1033890
@@ -41,10 +59,8 @@ def test_fullsize_graph_charge_and_csr_bit_exact(big, O):
     # undirected graph: every edge has its mirror
     i = np.repeat(np.arange(dev.N, dtype=np.int64), nn)[(nb >= 0).ravel()]; j = nb[nb >= 0].astype(np.int64)
     assert np.array_equal(np.sort(i * dev.N + j), np.sort(j * dev.N + i))
-    dev.updateCharge(buf, p.metals)
-    q = buf.site_charge.cpu().numpy()
+    q = _charges(big)
     assert np.array_equal(q, O.update_charge(nb, dev.site_element, p.metals, np.zeros(dev.N, np.int32)))
-    big["q"] = q
     sp = buf.sparsity(nc, nc)
     ref = O.csr_structure(nb, nc, nc)
     from test_gpu_parity import _from_ptr
@@ -52,7 +68,6 @@ def test_fullsize_graph_charge_and_csr_bit_exact(big, O):
     assert (sp.m, sp.nnz) == (dev.N - 2 * nc, len(ref["col"]))
     assert np.array_equal(_from_ptr(torch, sp.d_row_ptr, sp.m + 1), ref["row_ptr"])
     assert np.array_equal(_from_ptr(torch, sp.d_col, sp.nnz), ref["col"])
-    big["csr"] = ref
 
 
 def test_fullsize_assembly_bit_exact_and_solve_properties(big, O):
@@ -60,7 +75,7 @@ def test_fullsize_assembly_bit_exact_and_solve_properties(big, O):
     import torch
     from devicekmc_b200._capi import check
     p, dev, buf, nc, nb = big["p"], big["dev"], big["buf"], big["nc"], big["nb"]
-    q, csr = big["q"], big["csr"]
+    q, csr = _charges(big), O.csr_structure(nb, nc, nc)
     sp = buf.sparsity(nc, nc)
     Vd = 10.0
     val = torch.zeros(sp.nnz, dtype=torch.float64, device="cuda"); rhs = torch.zeros(sp.m, dtype=torch.float64, device="cuda")
@@ -84,17 +99,16 @@ def test_fullsize_assembly_bit_exact_and_solve_properties(big, O):
     assert dev.updatePotential(buf, p, -2.5 * Vd, n_contact=nc)["cg_converged"]
     phi2 = buf.site_potential_boundary.cpu().numpy()
     assert np.abs(phi2 + 2.5 * phi).max() <= TOL * np.abs(phi2).max()
-    # leave the 10 V state behind for the next tests
-    assert dev.updatePotential(buf, p, Vd, n_contact=nc)["cg_converged"]
-    big["pb"] = buf.site_potential_boundary.cpu().numpy()
-    big["pc"] = buf.site_potential_charge.cpu().numpy()
-    assert np.abs(big["pb"] - phi).max() <= TOL * np.abs(phi).max()
+    # back to 10 V from the -25 V solution: the same potential again (this is the state the next tests use)
+    big.pop("pb", None)
+    pb, _ = _potentials(big)
+    assert np.abs(pb - phi).max() <= TOL * np.abs(phi).max()
 
 
 def test_fullsize_pairwise_rows_and_superposition(big, O):
     from devicekmc_b200._capi import check
     p, dev, buf = big["p"], big["dev"], big["buf"]
-    q, pc = big["q"], big["pc"]
+    q, (_, pc) = _charges(big), _potentials(big)
     # oracle on bands of target rows (contacts, the oxide, the far end)
     for a, b in [(0, 400), (dev.N // 2, dev.N // 2 + 400), (dev.N - 400, dev.N)]:
         ref = O.poisson_gridless(dev.site_x, dev.site_y, dev.site_z, dev.lattice, p.pbc, q, p.sigma, p.k, rows=(a, b))
@@ -119,7 +133,7 @@ def test_fullsize_rate_table_and_first_events(big, O):
     import devicekmc_b200 as D
     from devicekmc_b200._capi import StepInfo, check, DKMC_ERR_RNG_EXHAUSTED
     p, dev, sim, buf, nb = big["p"], big["dev"], big["sim"], big["buf"], big["nb"]
-    q, pb, pc = big["q"], big["pb"], big["pc"]
+    q, (pb, pc) = _charges(big), _potentials(big)
     o_type, o_prob = O.rate_table(nb, sim.site_layer, dev.lattice, dev.pbc, dev.T_bg, sim.freq, dev.sigma, dev.k, dev.site_x,
                                   dev.site_y, dev.site_z, pb, pc, dev.site_element, q, buf.E_host.T)
     import torch
@@ -146,11 +160,25 @@ def test_fullsize_rate_table_and_first_events(big, O):
         O.set_event_limit(0)
     assert len(ev_ref) == n_ev
     u = D.RandomNumberGenerator(D.host.RND_SEED_KMC).getRandomNumbers(2 * n_ev)
-    info = StepInfo()
-    ev = np.zeros((n_ev, 4), np.int32)
-    st = lib.dkmc_execute_kmc_step(*args, u.ctypes.data_as(C.c_void_p), 2 * n_ev, ev.ctypes.data_as(C.c_void_p), n_ev,
-                                   C.byref(info))
-    assert st == DKMC_ERR_RNG_EXHAUSTED and info.n_events == n_ev and info.n_used == 2 * n_ev
-    assert np.array_equal(ev, ev_ref)                                   # (idx, i, j, type): bit-exact
-    assert np.array_equal(buf.site_element.cpu().numpy(), el_ref)
-    assert np.array_equal(buf.site_charge.cpu().numpy(), q_ref)
+    el0, q0 = buf.site_element.clone(), buf.site_charge.clone()
+    import time
+    # exact_mode 1: every selection goes through the exact sequential replay (the rare path of the
+    # default mode) — at this size it walks ~10^4 non-zero rows of 10^6 per selection
+    for exact_mode in (0, 1):
+        buf.site_element.copy_(el0); buf.site_charge.copy_(q0)
+        lib.dkmc_ctx_set_exact_select(h, exact_mode)
+        info = StepInfo()
+        ev = np.zeros((n_ev, 4), np.int32)
+        t0 = time.perf_counter()
+        try:
+            st = lib.dkmc_execute_kmc_step(*args, u.ctypes.data_as(C.c_void_p), 2 * n_ev, ev.ctypes.data_as(C.c_void_p),
+                                           n_ev, C.byref(info))
+        finally:
+            lib.dkmc_ctx_set_exact_select(h, 0)
+        assert st == DKMC_ERR_RNG_EXHAUSTED and info.n_events == n_ev and info.n_used == 2 * n_ev
+        assert np.array_equal(ev, ev_ref), exact_mode                    # (idx, i, j, type): bit-exact
+        assert np.array_equal(buf.site_element.cpu().numpy(), el_ref)
+        assert np.array_equal(buf.site_charge.cpu().numpy(), q_ref)
+        if exact_mode == 1:
+            assert info.n_exact_fallbacks == n_ev
+            assert time.perf_counter() - t0 < 5.0, "the exact replay must stay a millisecond-scale path"
