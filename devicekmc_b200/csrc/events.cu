@@ -213,11 +213,21 @@ __device__ void select_walk(const LoopArgs &a, double u, const double *errA, con
         if (lev == lv.n_levels - 1) {
             psum = __shfl_sync(0xffffffffu, inc, 31);
             number = u * psum;
-            // rounding-error bound of ANY summation order of the current rates, from the exponent
-            // histogram: E(tau) = sum_i min(x_i, tau) <= A[b_tau] + tau * B[b_tau]
+            // Rounding-error bound of the strictly sequential sum of the current rates, from the
+            // exponent histogram.  One rounded add errs by at most min(|a|, |b|) and by at most
+            // u * |result| (u = 2^-53), so every sequential prefix sum is within
+            //     E = sum_i min(x_i, u * Psum)  <=  E' = A[b_tau] + tau * B[b_tau],  tau = 2^-52 Psum
+            // of the exact one (E' takes tau = 2u Psum and the upper edge of every exponent bucket: E' >= E,
+            // up to 4 E).  The prefix sums of this walk go through ~35 rounded adds (five per warp scan and
+            // level) of partial sums <= Psum: within 35 tau of the exact ones.  The target u1 * Psum inherits
+            // the difference of the two totals (<= E + 35 tau) plus one rounding (<= tau).  The sequential
+            // search therefore brackets the same entry if the target is farther than 2 E + 72 tau from both
+            // bracketing prefix sums of this walk; delta = 8 E' + 128 tau keeps a factor >= 4 on the dominant
+            // term.  (An earlier 64 (E' + tau) sent 8x more selections than necessary to the exact replay,
+            // which at 4 M sites costs ~250 ms.)
             double tau = psum * 2.220446049250313e-16 * 1.000001;
             int bt = (int)((__double_as_longlong(tau) >> 52) & 0x7ff);
-            delta = 64.0 * (errA[bt] + tau * (double)errB[bt] + tau);
+            delta = 8.0 * (errA[bt] + tau * (double)errB[bt]) + 128.0 * tau;
         }
         double glob = prefix + inc;
         unsigned mask = __ballot_sync(0xffffffffu, glob > number);
