@@ -752,7 +752,18 @@ int dkmc_execute_kmc_step(dkmc_ctx *ctx, int N, int nn, const int *d_neigh_idx, 
 int dkmc_kmc_step_continue(dkmc_ctx *ctx, const double *uniforms, int n_uniforms, int *events_out, int max_events,
                            dkmc_step_info *info) {
     DKMC_REQUIRE(ctx != nullptr, "ctx");
-    return run_loop(ctx, uniforms, n_uniforms, events_out, max_events, info);
+    DKMC_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    int rc = run_loop(ctx, uniforms, n_uniforms, events_out, max_events, info);
+    if (rc != DKMC_OK && rc != DKMC_ERR_RNG_EXHAUSTED) return rc;
+    DKMC_CUDA(cudaEventRecord(ctx->ev_c, ctx->stream));
+    DKMC_CUDA(cudaEventSynchronize(ctx->ev_c));
+    if (info) {   // this call's share of the loop; the caller adds it to the first call's loop_ms
+        float b = 0;
+        cudaEventElapsedTime(&b, ctx->ev_b, ctx->ev_c);
+        info->rate_ms = 0.0;
+        info->loop_ms = b;
+    }
+    return rc;
 }
 
 int dkmc_last_event_tables(dkmc_ctx *ctx, const int **d_event_type, const double **d_event_prob) {

@@ -580,6 +580,7 @@ class KMCProcess:
                                             C.byref(info))
             check(st, allow=(_capi.DKMC_ERR_RNG_EXHAUSTED,))
             self.random_generator.advance(info.n_used)
+            loop_ms += info.loop_ms
         info.rate_ms, info.loop_ms = rate_ms, loop_ms
         self.last_info = info
         self.last_events = ev[: min(info.n_events, record_events)].copy() if record_events else ev[:0]

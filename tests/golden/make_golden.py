@@ -11,6 +11,7 @@ rnd_seed_kmc = 1, CPU build, 1 process):
   s_traj_ramp.npz  the kmc_main.cpp:136-279 loop on the shipped V_switch ramp, first 12 KMC steps:
                    per step Vd, executed (i, j) pairs, step time, sha256 of site_element/charge
   s_traj_6V.npz    the same loop at constant Vd = 6 V, 6 KMC steps (many events per step)
+  s_traj_6V_pbc.npz  the same at constant 6 V with pbc = 1 (periodic in y and z), 4 KMC steps
   s_snapshot.npz   Device::writeSnapshot (Device.cpp:236-252) of the s_step0 state: sha256 and size of the
                    file, its first and last lines
   s_cb_edge.npz    Device::setLaplacePotential (CPU branch, potential_solver.cpp:4-139) at Vd = 1.5 V:
@@ -34,8 +35,17 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def new_sim():
-    return R.RefSim(REF + "parameters.txt", REF + "reordered_device_2.5.xyz")
+def new_sim(pbc=0):
+    params = REF + "parameters.txt"
+    if pbc:
+        import re
+        import tempfile
+        txt, n = re.subn(r"pbc = 0", "pbc = 1", open(params).read())
+        assert n == 1
+        f = tempfile.NamedTemporaryFile("w", suffix="_parameters.txt", delete=False)
+        f.write(txt); f.close()
+        params = f.name
+    return R.RefSim(params, REF + "reordered_device_2.5.xyz")
 
 
 def step0():
@@ -95,9 +105,10 @@ def cb_edge():
     print("cb_edge written", cb[:2], cb[-2:])
 
 
-def trajectory(name, schedule, nsteps):
+def trajectory(name, schedule, nsteps, pbc=0):
     """schedule: list of (Vd, t) bias points as in kmc_main.cpp:136-279"""
-    s = new_sim()
+    s = new_sim(pbc)
+    assert s.pbc == pbc
     rec = dict(Vd=[], step_time=[], ev_ptr=[0], ev_ij=[], el_sha=[], q_sha=[], n_charged=[])
     count = 0
     for Vd, t in schedule:
@@ -118,6 +129,8 @@ def trajectory(name, schedule, nsteps):
             print(name, "step", count, "Vd", Vd, "events", len(ev), "dt", dt, flush=True)
         if count >= nsteps:
             break
+    rec["pbc"] = pbc
+    rec["degree"] = (s.neigh_idx() >= 0).sum(1).astype(np.int8)
     rec["pb_last"], rec["pc_last"] = s.potential_boundary(), s.potential_charge()
     rec["element_last"] = s.element().astype(np.int8)
     rec["ev_ij"] = np.concatenate(rec["ev_ij"]).astype(np.int32) if rec["ev_ptr"][-1] else np.zeros((0, 2), np.int32)
@@ -127,7 +140,7 @@ def trajectory(name, schedule, nsteps):
 if __name__ == "__main__":
     import devicekmc_b200.host as H
     p = H.KMCParameters.from_file(REF + "parameters.txt")
-    which = sys.argv[1:] or ["step0", "ramp", "6V", "cb_edge", "snapshot"]
+    which = sys.argv[1:] or ["step0", "ramp", "6V", "6V_pbc", "cb_edge", "snapshot"]
     if "step0" in which:
         step0()
     if "snapshot" in which:
@@ -138,3 +151,5 @@ if __name__ == "__main__":
         trajectory("s_traj_ramp.npz", list(zip(p.V_switch, p.t_switch)), 12)
     if "6V" in which:
         trajectory("s_traj_6V.npz", [(6.0, 1.0)], 6)
+    if "6V_pbc" in which:
+        trajectory("s_traj_6V_pbc.npz", [(6.0, 1.0)], 4, pbc=1)

@@ -129,14 +129,21 @@ def test_rng_stream_matches_reference(golden_step0, O):
     assert r2.getRandomNumber() == want[5]
 
 
-@pytest.mark.parametrize("name", ["s_traj_ramp.npz", "s_traj_6V.npz"])
+@pytest.mark.parametrize("name", ["s_traj_ramp.npz", "s_traj_6V.npz", "s_traj_6V_pbc.npz"])
 def test_oracle_trajectory_matches_reference(base_case, graph, O, name):
     """the kmc_main.cpp:175-279 loop with the oracle's stages, event for event against the
-    reference run (the potentials differ by the reference's own dgesv error, see above)"""
+    reference run (the potentials differ by the reference's own dgesv error, see above);
+    s_traj_6V_pbc: the same device periodic in y and z (pbc = 1)"""
     from devicekmc_b200.host import DEFAULT_LAYERS, RND_SEED_KMC
     g = np.load(os.path.join(GOLDEN, name))
-    nb, nn = graph
     p = base_case["p"]
+    pbc = int(g["pbc"]) if "pbc" in g.files else 0
+    if pbc:
+        nb, nn = O.neighbor_list(base_case["x"], base_case["y"], base_case["z"], base_case["lattice"], pbc, p.nn_dist, method=1)
+        assert np.array_equal((nb >= 0).sum(1), g["degree"].astype(np.int64))
+        assert (nb >= 0).sum() > (graph[0] >= 0).sum()               # the periodic images add neighbours
+    else:
+        nb, nn = graph
     nc = p.num_atoms_contact
     el = base_case["element"].copy()
     q = np.zeros(len(el), np.int32)
@@ -147,8 +154,10 @@ def test_oracle_trajectory_matches_reference(base_case, graph, O, name):
     for s, Vd in enumerate(g["Vd"][:6]):
         q = O.update_charge(nb, el, p.metals, q)
         phi, _ = O.background_potential(nb, nc, nc, el, q, p.metals, p.high_G, p.low_G, float(Vd), phi0=phi, refine=1)
-        pc = O.poisson_gridless(base_case["x"], base_case["y"], base_case["z"], base_case["lattice"], p.pbc, q, p.sigma, p.k)
-        et, ep = O.rate_table(nb, layer, base_case["lattice"], p.pbc, p.background_temp, p.freq, p.sigma, p.k,
+        pc = O.poisson_gridless(base_case["x"], base_case["y"], base_case["z"], base_case["lattice"], pbc, q, p.sigma, p.k)
+        if s == 0 and pbc:
+            assert np.array_equal(pc, g["pc0"])                       # periodic pairwise sum: bit-exact
+        et, ep = O.rate_table(nb, layer, base_case["lattice"], pbc, p.background_temp, p.freq, p.sigma, p.k,
                               base_case["x"], base_case["y"], base_case["z"], phi, pc, el, q, E)
         t, ev, el, q = O.kmc_events(nb, et, ep, el, q, p.freq, rng)
         assert np.array_equal(ev[:, 1:3], g["ev_ij"][g["ev_ptr"][s]:g["ev_ptr"][s + 1]]), f"step {s}"

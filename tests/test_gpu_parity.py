@@ -461,12 +461,15 @@ def test_kmc_step_continue_on_exhausted_uniforms(sim0, golden_step0, O, torch):
 
 
 # ------------------------------------------------------------------ trajectories vs the reference run
-@pytest.mark.parametrize("name", ["s_traj_ramp.npz", "s_traj_6V.npz"])
+@pytest.mark.parametrize("name", ["s_traj_ramp.npz", "s_traj_6V.npz", "s_traj_6V_pbc.npz"])
 def test_trajectory_matches_reference(base_case, torch, name):
     import hashlib
     from conftest import GOLDEN
     g = np.load(os.path.join(GOLDEN, name))
-    p, dev, sim, buf = make_sim(base_case)
+    pbc = int(g["pbc"]) if "pbc" in g.files else 0                  # s_traj_6V_pbc: periodic in y and z
+    p, dev, sim, buf = make_sim(base_case, pbc=pbc)
+    if pbc:
+        assert np.array_equal((dev.neigh_idx.reshape(dev.N, -1) >= 0).sum(1), g["degree"].astype(np.int64))
     nc = p.num_atoms_contact
     for s, Vd in enumerate(g["Vd"]):
         dev.updateCharge(buf, p.metals)
