@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) event_loop_kernel(LoopArgs a)
     __shared__ double errA[kHistBuckets];   // sum_{b' < b} count * 2^(b'+1)
     __shared__ int errB[kHistBuckets];      // sum_{b' >= b} count
     __shared__ int s_rows[2 + 2 * kMaxNN];
-    __shared__ int s_idx, s_flag, s_i, s_j, s_done, s_used, s_nev, s_nfb, s_nnone;
+    __shared__ int s_idx, s_flag, s_done, s_used, s_nev, s_nfb, s_nnone;
     __shared__ double s_psum, s_delta, s_time;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = kLoopThreads / 32;
