@@ -660,8 +660,10 @@ static int get_tiling(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const
 }
 
 static int vec_grid(const dkmc_ctx *ctx, int m) {
+    // CTAs per SM of the grid-stride vector kernels; DKMC_VEC_CPS is a tuning aid (tools/vec_grid_experiment.py)
+    static const int cps = [] { const char *e = getenv("DKMC_VEC_CPS"); int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
     int g = ceil_div((m + 1) / 2, kVecThreads);
-    int cap = ctx->num_sms * 16;
+    int cap = ctx->num_sms * cps;
     return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
