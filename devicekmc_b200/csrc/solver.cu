@@ -660,8 +660,11 @@ static int get_tiling(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const
 }
 
 static int vec_grid(const dkmc_ctx *ctx, int m) {
-    // CTAs per SM of the grid-stride vector kernels; DKMC_VEC_CPS is a tuning aid (tools/vec_grid_experiment.py)
-    static const int cps = [] { const char *e = getenv("DKMC_VEC_CPS"); int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+    // CTAs per SM of the grid-stride vector kernels: 5 = what is resident at once (48 registers x 256 threads),
+    // so every CTA makes 2-3 passes and the fixed cost per CTA (scalar loads, block reduction, ticket) and the
+    // final sum over the partials shrink 2.6x.  Measured at 1 M sites (tools/vec_grid_experiment.py):
+    // 106 us per CG iteration instead of 111 (one pass per thread, 16 per SM), 152 instead of 157 overlapped.
+    static const int cps = [] { const char *e = getenv("DKMC_VEC_CPS"); int v = e ? atoi(e) : 5; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
     int g = ceil_div((m + 1) / 2, kVecThreads);
     int cap = ctx->num_sms * cps;
     return g < 1 ? 1 : (g > cap ? cap : g);
