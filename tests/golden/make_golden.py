@@ -11,6 +11,11 @@ rnd_seed_kmc = 1, CPU build, 1 process):
   s_traj_ramp.npz  the kmc_main.cpp:136-279 loop on the shipped V_switch ramp, first 12 KMC steps:
                    per step Vd, executed (i, j) pairs, step time, sha256 of site_element/charge
   s_traj_6V.npz    the same loop at constant Vd = 6 V, 6 KMC steps (many events per step)
+  s_rates_ions.npz crafted state: 80 interstitial sites of the oxide turned into oxygen ions (Od) next to the
+                   5 % vacancies, then updateCharge + potentials at 3 V + the rate table: pins the recombination
+                   and ion-diffusion rates (event types 1 and 3), which short trajectories hardly reach
+  s_traj_10V.npz   the same at constant 10 V, 8 KMC steps: generation, then diffusion of the generated
+                   oxygen ions (the one event type the other trajectories never execute)
   s_traj_6V_pbc.npz  the same at constant 6 V with pbc = 1 (periodic in y and z), 4 KMC steps
   s_snapshot.npz   Device::writeSnapshot (Device.cpp:236-252) of the s_step0 state: sha256 and size of the
                    file, its first and last lines
@@ -97,6 +102,27 @@ def snapshot():
     print("snapshot written", len(raw), "bytes;", lines[2], "|", lines[3002])
 
 
+def rates_ions():
+    s = new_sim()
+    el = s.element()
+    x, _, _ = s.positions()
+    cand = np.nonzero((el == 0) & (x > 3.0) & (x < 48.0))[0]          # DEFECT (empty interstitial) sites of the oxide
+    pick = np.random.default_rng(11).choice(cand, 80, replace=False)
+    el[pick] = 1                                                        # OXYGEN_DEFECT
+    s.set_element(el)
+    s.update_charge()
+    Vd = 3.0
+    s.background_potential(Vd)
+    s.poisson_gridless()
+    et, ep = s.rate_table()
+    nz = np.nonzero(et != 4)[0]
+    np.savez_compressed(os.path.join(OUT, "s_rates_ions.npz"), Vd=Vd, element=el.astype(np.int8),
+                        charge=s.charge().astype(np.int8), potential_boundary=s.potential_boundary(),
+                        potential_charge=s.potential_charge(), ev_idx=nz.astype(np.int32), ev_type=et[nz].astype(np.int8),
+                        ev_prob=ep[nz])
+    print("rates_ions written; types:", {int(t): int((et[nz] == t).sum()) for t in np.unique(et[nz])})
+
+
 def cb_edge():
     s = new_sim()
     Vd = 1.5
@@ -140,9 +166,11 @@ def trajectory(name, schedule, nsteps, pbc=0):
 if __name__ == "__main__":
     import devicekmc_b200.host as H
     p = H.KMCParameters.from_file(REF + "parameters.txt")
-    which = sys.argv[1:] or ["step0", "ramp", "6V", "6V_pbc", "cb_edge", "snapshot"]
+    which = sys.argv[1:] or ["step0", "ramp", "6V", "10V", "6V_pbc", "cb_edge", "snapshot", "rates_ions"]
     if "step0" in which:
         step0()
+    if "rates_ions" in which:
+        rates_ions()
     if "snapshot" in which:
         snapshot()
     if "cb_edge" in which:
@@ -151,5 +179,7 @@ if __name__ == "__main__":
         trajectory("s_traj_ramp.npz", list(zip(p.V_switch, p.t_switch)), 12)
     if "6V" in which:
         trajectory("s_traj_6V.npz", [(6.0, 1.0)], 6)
+    if "10V" in which:
+        trajectory("s_traj_10V.npz", [(10.0, 1.0)], 8)
     if "6V_pbc" in which:
         trajectory("s_traj_6V_pbc.npz", [(6.0, 1.0)], 4, pbc=1)

@@ -117,6 +117,32 @@ def test_oracle_rate_table_bit_exact_vs_reference(base_case, golden_step0, graph
     assert np.array_equal(et, g_type) and np.array_equal(ep, g_prob)
 
 
+def test_oracle_rates_with_oxygen_ions_bit_exact_vs_reference(base_case, graph, O):
+    """crafted state (tests/golden/make_golden.py rates_ions): 80 oxygen ions in the oxide, so that the
+    table holds recombination (type 1) and ion-diffusion (type 3) entries as well — all four rate
+    formulas of KMCProcess.cpp:67-164 against the reference's own table, bit for bit"""
+    from devicekmc_b200.host import DEFAULT_LAYERS
+    g = np.load(os.path.join(GOLDEN, "s_rates_ions.npz"))
+    nb, nn = graph
+    p = base_case["p"]
+    el = g["element"].astype(np.int32)
+    assert np.count_nonzero(el == 1) == 80
+    q = O.update_charge(nb, el, p.metals, np.zeros(len(el), np.int32))
+    assert np.array_equal(q, g["charge"].astype(np.int32))
+    assert (q[el == 1] == -2).any()
+    layer = O.site_layers(base_case["x"], [l.start_x for l in DEFAULT_LAYERS], [l.end_x for l in DEFAULT_LAYERS])
+    E = np.array([[l.E_gen_0, l.E_rec_1, l.E_diff_2, l.E_diff_3] for l in DEFAULT_LAYERS])
+    et, ep = O.rate_table(nb, layer, base_case["lattice"], p.pbc, p.background_temp, p.freq, p.sigma, p.k, base_case["x"],
+                          base_case["y"], base_case["z"], g["potential_boundary"], g["potential_charge"], el, q, E)
+    g_type = np.full(len(et), 4, np.int32); g_prob = np.zeros(len(ep))
+    g_type[g["ev_idx"]] = g["ev_type"]; g_prob[g["ev_idx"]] = g["ev_prob"]
+    assert set(np.unique(g["ev_type"]).tolist()) == {0, 1, 2, 3}
+    assert np.array_equal(et, g_type) and np.array_equal(ep, g_prob)
+    # the pairwise potential of this state (negative and positive charges) is bit-exact as well
+    pc = O.poisson_gridless(base_case["x"], base_case["y"], base_case["z"], base_case["lattice"], p.pbc, q, p.sigma, p.k)
+    assert np.array_equal(pc, g["potential_charge"])
+
+
 def test_rng_stream_matches_reference(golden_step0, O):
     from devicekmc_b200.host import RandomNumberGenerator, RND_SEED_KMC
     want = golden_step0["kmc_rng_first16"]
@@ -129,7 +155,7 @@ def test_rng_stream_matches_reference(golden_step0, O):
     assert r2.getRandomNumber() == want[5]
 
 
-@pytest.mark.parametrize("name", ["s_traj_ramp.npz", "s_traj_6V.npz", "s_traj_6V_pbc.npz"])
+@pytest.mark.parametrize("name", ["s_traj_ramp.npz", "s_traj_6V.npz", "s_traj_6V_pbc.npz", "s_traj_10V.npz"])
 def test_oracle_trajectory_matches_reference(base_case, graph, O, name):
     """the kmc_main.cpp:175-279 loop with the oracle's stages, event for event against the
     reference run (the potentials differ by the reference's own dgesv error, see above);
@@ -151,7 +177,8 @@ def test_oracle_trajectory_matches_reference(base_case, graph, O, name):
     E = np.array([[l.E_gen_0, l.E_rec_1, l.E_diff_2, l.E_diff_3] for l in DEFAULT_LAYERS])
     rng = O.Rng(RND_SEED_KMC)
     phi = np.zeros(len(el))
-    for s, Vd in enumerate(g["Vd"][:6]):
+    executed = set()
+    for s, Vd in enumerate(g["Vd"][:8]):
         q = O.update_charge(nb, el, p.metals, q)
         phi, _ = O.background_potential(nb, nc, nc, el, q, p.metals, p.high_G, p.low_G, float(Vd), phi0=phi, refine=1)
         pc = O.poisson_gridless(base_case["x"], base_case["y"], base_case["z"], base_case["lattice"], pbc, q, p.sigma, p.k)
@@ -163,6 +190,11 @@ def test_oracle_trajectory_matches_reference(base_case, graph, O, name):
         assert np.array_equal(ev[:, 1:3], g["ev_ij"][g["ev_ptr"][s]:g["ev_ptr"][s + 1]]), f"step {s}"
         assert abs(t - g["step_time"][s]) <= 1e-7 * abs(g["step_time"][s])
         assert hashlib.sha256(el.tobytes()).hexdigest() == str(g["el_sha"][s])
+        executed.update(ev[:, 3].tolist())
+    if name == "s_traj_ramp.npz":
+        assert {0, 1, 2} <= executed                 # generation, recombination, vacancy diffusion
+    if name == "s_traj_10V.npz":
+        assert g["ev_ptr"][1] >= 20                  # many events inside one step (stale table, conflicts zeroed)
 
 
 def test_oracle_event_selection_edge_cases(O):
