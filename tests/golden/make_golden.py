@@ -11,6 +11,8 @@ rnd_seed_kmc = 1, CPU build, 1 process):
   s_traj_ramp.npz  the kmc_main.cpp:136-279 loop on the shipped V_switch ramp, first 12 KMC steps:
                    per step Vd, executed (i, j) pairs, step time, sha256 of site_element/charge
   s_traj_6V.npz    the same loop at constant Vd = 6 V, 6 KMC steps (many events per step)
+  s_substoich.npz  Device::makeSubstoichiometric (Device.cpp:202-233) for other seeds / concentrations than the
+                   shipped (4, 0.05): sha256 of site_element after the reference's draw
   s_rates_ions.npz crafted state: 80 interstitial sites of the oxide turned into oxygen ions (Od) next to the
                    5 % vacancies, then updateCharge + potentials at 3 V + the rate table: pins the recombination
                    and ion-diffusion rates (event types 1 and 3), which short trajectories hardly reach
@@ -102,6 +104,26 @@ def snapshot():
     print("snapshot written", len(raw), "bytes;", lines[2], "|", lines[3002])
 
 
+def substoich():
+    import re
+    import tempfile
+    base = open(REF + "parameters.txt").read()
+    seeds, concs, shas, nvac = [], [], [], []
+    for seed, conc in [(1, 0.02), (7, 0.1), (123, 0.05), (4, 0.2)]:
+        txt, n1 = re.subn(r"rnd_seed = \d+", f"rnd_seed = {seed}", base)
+        txt, n2 = re.subn(r"initial_vacancy_concentration = [0-9.]+", f"initial_vacancy_concentration = {conc}", txt)
+        assert n1 == 1 and n2 == 1
+        f = tempfile.NamedTemporaryFile("w", suffix="_parameters.txt", delete=False)
+        f.write(txt); f.close()
+        s = R.RefSim(f.name, REF + "reordered_device_2.5.xyz")
+        assert s.rnd_seed == seed
+        el = s.element()
+        seeds.append(seed); concs.append(conc); shas.append(sha(el)); nvac.append(int((el == 2).sum()))
+        print("substoich", seed, conc, nvac[-1], shas[-1][:12])
+    np.savez_compressed(os.path.join(OUT, "s_substoich.npz"), seed=np.array(seeds), conc=np.array(concs),
+                        sha=np.array(shas), n_vacancies=np.array(nvac))
+
+
 def rates_ions():
     s = new_sim()
     el = s.element()
@@ -166,9 +188,11 @@ def trajectory(name, schedule, nsteps, pbc=0):
 if __name__ == "__main__":
     import devicekmc_b200.host as H
     p = H.KMCParameters.from_file(REF + "parameters.txt")
-    which = sys.argv[1:] or ["step0", "ramp", "6V", "10V", "6V_pbc", "cb_edge", "snapshot", "rates_ions"]
+    which = sys.argv[1:] or ["step0", "ramp", "6V", "10V", "6V_pbc", "cb_edge", "snapshot", "rates_ions", "substoich"]
     if "step0" in which:
         step0()
+    if "substoich" in which:
+        substoich()
     if "rates_ions" in which:
         rates_ions()
     if "snapshot" in which:

@@ -251,6 +251,22 @@ def test_snapshot_file_matches_reference_writer(base_case, golden_step0, tmp_pat
     assert hashlib.sha256(raw).hexdigest() == str(g["sha256"])
 
 
+def test_substoichiometric_draw_matches_reference_for_other_seeds():
+    """bench.substoichiometric (the host-side restatement of Device::makeSubstoichiometric that prepares every
+    benchmark device) against the reference's own draw for seeds / concentrations other than the shipped ones"""
+    import dataclasses
+    import bench
+    from devicekmc_b200 import structures as S
+    from devicekmc_b200.host import KMCParameters, VACANCY
+    g = np.load(os.path.join(GOLDEN, "s_substoich.npz"))
+    el0 = S.load_base_cell()[0]
+    for seed, conc, want, nv in zip(g["seed"], g["conc"], g["sha"], g["n_vacancies"]):
+        p = dataclasses.replace(KMCParameters(), rnd_seed=int(seed), initial_vacancy_concentration=float(conc))
+        el = bench.substoichiometric(el0, p)
+        assert int((el == VACANCY).sum()) == int(nv)
+        assert hashlib.sha256(np.ascontiguousarray(el, np.int32).tobytes()).hexdigest() == str(want), (seed, conc)
+
+
 def test_tiled_device_structure(O):
     from devicekmc_b200 import structures as S
     el, x, y, z, lat, nc = S.tile_device(2, 2)
