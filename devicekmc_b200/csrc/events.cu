@@ -218,13 +218,14 @@ __device__ void select_walk(const LoopArgs &a, double u, const double *errA, con
             // u * |result| (u = 2^-53), so every sequential prefix sum is within
             //     E = sum_i min(x_i, u * Psum)  <=  E' = A[b_tau] + tau * B[b_tau],  tau = 2^-52 Psum
             // of the exact one (E' takes tau = 2u Psum and the upper edge of every exponent bucket: E' >= E,
-            // up to 4 E).  The prefix sums of this walk go through ~35 rounded adds (five per warp scan and
-            // level) of partial sums <= Psum: within 35 tau of the exact ones.  The target u1 * Psum inherits
-            // the difference of the two totals (<= E + 35 tau) plus one rounding (<= tau).  The sequential
-            // search therefore brackets the same entry if the target is farther than 2 E + 72 tau from both
-            // bracketing prefix sums of this walk; delta = 8 E' + 128 tau keeps a factor >= 4 on the dominant
-            // term.  (An earlier 64 (E' + tau) sent 8x more selections than necessary to the exact replay,
-            // which at 4 M sites costs ~250 ms.)
+            // up to 4 E).  A prefix sum of this walk goes through at most ~45 rounded adds of partial sums
+            // <= Psum (per level five in the warp scan and one for the running prefix, a few more inside the
+            // row): within 45 tau of the exact one.  The target u1 * Psum inherits the difference of the two
+            // totals (<= E + 36 tau) plus one rounding (<= tau).  The sequential search therefore brackets the
+            // same entry if the target is farther than 2 E + 82 tau from both bracketing prefix sums of this
+            // walk; delta = 8 E' + 128 tau keeps a factor >= 4 on the dominant term.  (An earlier
+            // 64 (E' + tau) sent 8x more selections than necessary to the exact replay, which at 4 M sites
+            // costs ~250 ms.  tests/test_cpu_selection_margin.py replays this logic on the CPU.)
             double tau = psum * 2.220446049250313e-16 * 1.000001;
             int bt = (int)((__double_as_longlong(tau) >> 52) & 0x7ff);
             delta = 8.0 * (errA[bt] + tau * (double)errB[bt]) + 128.0 * tau;
