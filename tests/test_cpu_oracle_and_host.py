@@ -296,6 +296,23 @@ def test_capi_library_exports_every_declared_symbol():
     assert lib.dkmc_version() == 100
 
 
+def test_capi_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/dkmc.h must compile as C11 (no C++ or torch types in any
+    signature) and link against the library from a C program"""
+    import subprocess
+    from devicekmc_b200 import _capi
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "dkmc.h"\n'
+                   'int main(void) { dkmc_ctx *c = 0; (void)c; return dkmc_version() == DKMC_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    exe = tmp_path / "cabi"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ldkmc_b200",
+                           f"-Wl,-rpath,{libdir}", "-Wl,--allow-shlib-undefined"])
+    assert subprocess.run([str(exe)]).returncode == 0          # dkmc_version() needs no GPU
+
+
 def test_product_path_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
