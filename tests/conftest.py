@@ -53,3 +53,18 @@ def base_case(golden_step0):
             num_v -= 1
     assert np.array_equal(el, golden_step0["element"].astype(np.int32)), "substoichiometric draw differs from the reference"
     return dict(element=el, x=x, y=y, z=z, lattice=lat, n_contact=nc, p=p)
+
+
+def build_cpp_example(out_dir):
+    """compiles examples/kmc_loop.cpp (a C++ host over the C-ABI, no reference headers) against the in-tree
+    library; returns the path of the executable"""
+    import subprocess
+    from devicekmc_b200 import _capi
+    exe = os.path.join(str(out_dir), "kmc_loop")
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(cuda, "include"), os.path.join(ROOT, "examples", "kmc_loop.cpp"), "-o", exe,
+                           "-L", libdir, "-ldkmc_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart",
+                           f"-Wl,-rpath,{libdir}"])
+    return exe

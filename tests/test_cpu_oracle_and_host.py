@@ -313,6 +313,22 @@ def test_capi_header_is_plain_c(tmp_path):
     assert subprocess.run([str(exe)]).returncode == 0          # dkmc_version() needs no GPU
 
 
+def test_cpp_example_builds_and_fails_loudly_without_gpu(base_case, tmp_path):
+    """examples/kmc_loop.cpp: every call of the loop type-checks against include/dkmc.h, the program links,
+    and without a GPU it stops at dkmc_ctx_create with the library's error text (no CPU fallback)"""
+    import subprocess
+    import torch
+    from conftest import build_cpp_example
+    from devicekmc_b200.host import write_xyz
+    exe = build_cpp_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: tests/test_gpu_zz_ions.py runs the example")
+    xyz = tmp_path / "device.xyz"
+    write_xyz(str(xyz), base_case["element"], base_case["x"], base_case["y"], base_case["z"])
+    r = subprocess.run([exe, str(xyz), "108.97557", "25.575", "25.575", "144", "6.0", "2"], capture_output=True, text=True)
+    assert r.returncode == 1 and "dkmc_ctx_create" in r.stderr and "no CUDA device" in r.stderr, (r.stdout, r.stderr)
+
+
 def test_product_path_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():

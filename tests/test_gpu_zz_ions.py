@@ -66,3 +66,23 @@ def test_rate_table_charges_and_events_with_oxygen_ions(base_case):
     assert np.array_equal(sim.last_events, ev_ref)
     assert np.array_equal(buf.site_element.cpu().numpy(), el_ref) and np.array_equal(buf.site_charge.cpu().numpy(), q_ref)
     assert abs(t - t_ref) <= 1e-12 * abs(t_ref)
+
+
+def test_cpp_host_example_reproduces_the_reference_trajectory(base_case, tmp_path):
+    """examples/kmc_loop.cpp — a C++ host over the C-ABI with std::mt19937 as the reference uses it — on the
+    shipped device at constant 6 V: the KMC times of the reference's CPU run (s_traj_6V.npz), step for step"""
+    import re
+    import subprocess
+    from conftest import build_cpp_example
+    from devicekmc_b200.host import write_xyz
+    g = np.load(os.path.join(GOLDEN, "s_traj_6V.npz"))
+    exe = build_cpp_example(tmp_path)
+    xyz = tmp_path / "device.xyz"
+    write_xyz(str(xyz), base_case["element"], base_case["x"], base_case["y"], base_case["z"])
+    r = subprocess.run([exe, str(xyz), "108.97557", "25.575", "25.575", "144", "6.0", str(len(g["Vd"]))],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    times = [float(v) for v in re.findall(r"KMC time is: (\S+)", r.stdout)]
+    events = [int(v) for v in re.findall(r"(\d+) events", r.stdout)]
+    assert events == np.diff(g["ev_ptr"]).tolist()
+    assert np.allclose(times, np.cumsum(g["step_time"]), rtol=2e-5)          # printed with 6 significant digits
