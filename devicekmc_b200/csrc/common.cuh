@@ -51,7 +51,7 @@ enum Slot : int {
     S_SP_CNT, S_SCAN_BLOCK,
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
-    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_PCOL, S_CG_PDIAG, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
+    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_S, S_CL_REC, S_PCG_SYNC, S_PCG_PROF, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
     S_NB_HOSTPOS, S_NB_HOSTTAB, S_PW_PREVQ, S_PW_DQ, S_SNAP_STAGE, S_EV_NZROWS, S_EV_BATCHSUM,
     S_LAST
 };
@@ -62,31 +62,6 @@ struct SpmvTiling {
     int m = 0, nnz = 0;
     int num_tiles = 0;
     int *d_tile_row = nullptr;     // [num_tiles+1] first row of each nnz tile
-};
-
-// window-staged format of K for the CG's SpMV (spmv_win.cuh), built once per sparsity pattern
-struct WinFormat {
-    const int *row_ptr = nullptr, *col = nullptr;  // key
-    int m = 0, nnz = 0, num_tiles = 0;
-    bool ok = false;                     // every tile fits the format's limits
-    int fail_bits = 0, max_chunk = 0;
-    size_t blob_bytes = 0;
-    unsigned char *blobs = nullptr;      // per tile: header, runs, codes, row starts, row order, diagonal
-    void *plan = nullptr;                // int4 per tile: (blob offset / 128, blob bytes, window doubles, -)
-    unsigned short *code_base = nullptr; // static, CSR-indexed: window position | diagonal bit
-    int *code_pos = nullptr;             // per row: halfword index into `blobs` of the row's first code
-    int *diag_pos = nullptr;             // per row: double index into `blobs` of the row's diagonal entry
-    const double *val_tag = nullptr;     // the assembled CSR values the blobs correspond to
-    double m_high = 0.0, m_low = 0.0;    // -high_G, -low_G
-};
-
-// packed CSR of the matrix the context assembled last (solver.cu): 4 bytes per non-zero
-struct PackedCsr {
-    int *pcol = nullptr;               // column | bit 31 high_G | bit 30 diagonal
-    double *diag = nullptr;            // per-row diagonal of K
-    const int *row_ptr = nullptr;      // the pattern it belongs to
-    const double *val_tag = nullptr;   // the CSR values it mirrors
-    double m_high = 0.0, m_low = 0.0;  // -high_G, -low_G
 };
 
 }  // namespace dkmc
@@ -108,10 +83,6 @@ struct dkmc_ctx {
         bool valid = false;
     } grid;
     dkmc::SpmvTiling tiling;
-    dkmc::WinFormat win;
-    dkmc::PackedCsr packed;
-    int use_packed_spmv = 0;   // opt-in (dkmc_ctx_set_packed_spmv): measured no faster, the SpMV is gather-bound
-    int use_window_spmv = 0;   // opt-in (dkmc_ctx_set_window_spmv / DKMC_WINDOW_SPMV=1)
     // event loop state for dkmc_kmc_step_continue
     struct {
         int N = 0, nn = 0;
@@ -126,6 +97,9 @@ struct dkmc_ctx {
     } ev;
     int exact_select = 0;
     void *dist = nullptr;  // DistState (NCCL communicator) when running slab-partitioned
+    int legacy_cg = 0;     // 1: one kernel per CG operation (round-1 path) instead of the persistent PCG
+    void *selfwin = nullptr;   // SelfWindow (solver.cu): the persistent PCG's window on one GPU
+    int pw_regs_per_thread = 80;   // registers of the overlapped pairwise kernel (pairwise.cu refreshes it)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     // side stream: the pairwise sum (FP64-bound) runs there while the CG (HBM-bound) runs on `stream`
     cudaStream_t side_stream = nullptr;
@@ -158,7 +132,7 @@ struct dkmc_ctx {
 
 namespace dkmc {
 
-void free_win_format(dkmc_ctx *ctx);
+void free_solver_state(dkmc_ctx *ctx);   // solver.cu: the single-GPU window of the persistent PCG
 
 // returns a device buffer of at least `bytes` for `slot` (contents NOT preserved on growth)
 int ensure_slot(dkmc_ctx *ctx, int slot, size_t bytes, void **out);

@@ -21,14 +21,6 @@ int window_carveout() {
     return pct;
 }
 
-void free_win_format(dkmc_ctx *ctx) {
-    WinFormat &w = ctx->win;
-    void *ptrs[5] = {w.blobs, w.plan, w.code_base, w.code_pos, w.diag_pos};
-    for (void *p : ptrs)
-        if (p) cudaFree(p);
-    w = WinFormat();
-}
-
 int ensure_slot(dkmc_ctx *ctx, int slot, size_t bytes, void **out) {
     if (bytes == 0) bytes = 16;
     if (ctx->slot_cap[slot] < bytes) {
@@ -117,8 +109,7 @@ int dkmc_ctx_create(dkmc_ctx **out) {
     DKMC_CUDA(cudaStreamCreateWithFlags(&ctx->io_stream, cudaStreamNonBlocking));
     DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap_staged, cudaEventDisableTiming));
     DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap_done, cudaEventDisableTiming));
-    if (const char *e = getenv("DKMC_PACKED_SPMV")) ctx->use_packed_spmv = atoi(e) ? 1 : 0;
-    if (const char *e = getenv("DKMC_WINDOW_SPMV")) ctx->use_window_spmv = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("DKMC_LEGACY_CG")) ctx->legacy_cg = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DKMC_PW_SIDE_BPS")) { int v = atoi(e); if (v > 0) ctx->pw_side_blocks_per_sm = v; }
     *out = ctx;
     return DKMC_OK;
@@ -137,7 +128,7 @@ int dkmc_ctx_destroy(dkmc_ctx *ctx) {
     for (int s = 0; s < kNumSlots; ++s)
         if (ctx->slot_ptr[s]) cudaFree(ctx->slot_ptr[s]);
     if (ctx->tiling.d_tile_row) cudaFree(ctx->tiling.d_tile_row);
-    free_win_format(ctx);
+    free_solver_state(ctx);
     if (ctx->d_layerE) cudaFree(ctx->d_layerE);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);

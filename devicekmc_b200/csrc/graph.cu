@@ -403,7 +403,6 @@ int dkmc_free_sparsity(dkmc_ctx *ctx, dkmc_sparsity *sp) {
         cudaFree(ctx->tiling.d_tile_row);
         ctx->tiling = SpmvTiling();
     }
-    free_win_format(ctx);
     return DKMC_OK;
 }
 

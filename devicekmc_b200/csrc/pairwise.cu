@@ -561,6 +561,18 @@ static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm
                            const double *d_lattice, const double *d_sigma, const double *d_k, const double *d_x,
                            const double *d_y, const double *d_z, const ChargedSite *src, const int *src_idx,
                            const int *total, int *tile_counter, double *d_out, const PwCells *cells, int accumulate = 0) {
+    if (shared_sms) {
+        // what the persistent PCG sizes its grid by: the registers this kernel holds per thread
+        static int regs[3] = {0, 0, 0};
+        const int which = cells ? 0 : (pbc ? 1 : 2);
+        if (!regs[which]) {
+            cudaFuncAttributes fa;
+            cudaError_t e = cells ? cudaFuncGetAttributes(&fa, pairwise_cells_kernel)
+                                  : (pbc ? cudaFuncGetAttributes(&fa, pairwise_kernel<true>) : cudaFuncGetAttributes(&fa, pairwise_kernel<false>));
+            regs[which] = e == cudaSuccess ? fa.numRegs : 96;
+        }
+        ctx->pw_regs_per_thread = regs[which];
+    }
     if (cells) {  // one target per thread
         int grid = ctx->num_sms * blocks_per_sm;
         int *sm_count = nullptr;

@@ -1,0 +1,418 @@
+// devicekmc-b200 — the preconditioned CG of a5 as ONE persistent kernel per solve, for one GPU and for
+// x-slab partitioned ranks alike (replaces the reference's launch sequence, iterative_solvers_gpu.cu:424-455:
+// cusparseSpMV + 8 cuBLAS-1 calls + 4 host-synchronous scalar reads per iteration).
+//
+// Recurrence: Chronopoulos-Gear CG — algebraically the CG of iterative_solvers_gpu.cu:424-455 on the
+// preconditioned system, rearranged so that both inner products of an iteration are taken at the same
+// point (one reduction per iteration instead of two):
+//     p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M^-1 r ; w = A u
+//     gamma = (r,u), delta = (w,u)            <- the ONE reduction
+//     beta = gamma / gamma_old ; alpha = gamma / (delta - beta gamma / alpha_old)
+// M^-1 = D^-1 + W E^-1 W^T (Jacobi + one coarse unknown per uncharged-vacancy cluster, solver.cu).  The cluster
+// sums W^T r follow the same recurrences (W^T s = W^T w + beta W^T s, W^T r -= alpha W^T s) from W^T w, which is
+// computed beside the SpMV and travels in the same reduction — so clusters may straddle slab faces and the
+// preconditioner costs no extra synchronisation.
+//
+// An iteration is two phases separated by grid barriers:
+//   V  vector phase over the own rows (p, s, x, r, u; gamma partial); boundary rows of u are stored straight
+//      into the neighbours' windows over NVLink.  Barrier H: local arrival counter; the last CTA raises the
+//      halo flags at the neighbours; every CTA waits for the local release and the neighbours' flags.
+//   S  SpMV w = A u over the own nnz tiles (delta partial) + cluster rows (W^T w partial).  Barrier R: the
+//      last CTA to arrive adds the CTA partials in index order and stores [gamma, delta, W^T w] into every
+//      rank's slot, then raises its flag everywhere; every CTA waits for all ranks' flags in its own window
+//      and adds the slots in rank order — identical bits on all ranks, and no second local barrier.
+// One GPU is the same code with world = 1 (the "window" is then ordinary device memory).
+// Scalars live in registers of every CTA; the host launches once per solve and reads the result.
+//
+// Memory-model notes: vectors that change inside the kernel (u, r, p, s, w, x) are read with plain loads
+// (never __ldg / ld.global.nc: the kernel outlives the usual per-launch L1 invalidation); the acquire loads
+// that end every barrier invalidate L1, so plain loads afterwards observe what other SMs / GPUs wrote.
+#pragma once
+// (included by solver.cu inside namespace dkmc, after the peer-window plumbing)
+
+struct PcgSync {
+    unsigned int arrive_h, arrive_r;   // arrival counters of the two barrier kinds (reset by the last arriver)
+    unsigned long long gen_h;          // local release of barrier H: the halo sequence number reached
+    unsigned long long pad;
+};
+
+struct PcgArgs {
+    int m, ra, rb, t0, t1, n_cl, max_iter;
+    const int *row_ptr, *col;
+    const double *val, *dinv, *b;
+    const int4 *tile_info;
+    double *x, *r, *w, *p, *s;           // full-length vectors; only the own rows [ra, rb) are touched
+    Precond P;                           // cluster tables (pos may be null: plain Jacobi)
+    double *cs, *cr;                     // [2][n_cl] cluster-sum recurrences W^T s, W^T r (replicated)
+    double *payload;                     // [4 + 2 n_cl] this rank's contribution to a reduction
+    double *partials;                    // [3][gridDim] CTA partial sums
+    PcgSync *sync;
+    CgScalars *sc;
+    double tol;
+    unsigned long long rseq0, hseq0;     // sequence numbers already used by earlier solves
+    P2pPeers peers;
+    P2pHalo halo;
+    long long *prof;                     // optional [8]: time spent by CTA 0 per phase (ns)
+};
+
+constexpr int kPcgFlagR = 4, kPcgFlagH = 6;   // flag banks of the persistent kernel (0-3: the per-op kernels)
+
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long pcg_now() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// second bank of reduction slots (the per-op kernels keep the first)
+__device__ __forceinline__ double *pcg_slot(const P2pPeers &P, int at_rank, int buf, int of_rank) {
+    return reinterpret_cast<double *>(P.base[at_rank] + P.red2_off) + ((size_t)buf * P.world + of_rank) * kP2pRedCap;
+}
+
+// sum over the ranks (in rank order) of entry j of the reduction with parity `buf`, as it arrived here
+__device__ __forceinline__ double pcg_reduced(const P2pPeers &P, int buf, int j) {
+    double acc = 0.0;
+    for (int q = 0; q < P.world; ++q) acc += *(reinterpret_cast<const volatile double *>(pcg_slot(P, P.rank, buf, q)) + j);
+    return acc;
+}
+
+__device__ __forceinline__ bool pcg_push(const P2pHalo &H, const P2pPeers &P, int i, double v) {
+    bool pushed = false;
+    for (int sgm = 0; sgm < H.n_send; ++sgm)
+        if (i >= H.send_begin[sgm] && i < H.send_end[sgm]) {
+            reinterpret_cast<double *>(P.base[H.send_peer[sgm]])[i] = v;
+            pushed = true;
+        }
+    return pushed;
+}
+
+// Barrier H: the own rows of u (and the boundary rows pushed to the neighbours) are complete on return,
+// and so are the neighbours' boundary rows in this rank's window.
+__device__ __forceinline__ void pcg_barrier_halo(const PcgArgs &a, unsigned long long hseq, bool pushed) {
+    const P2pPeers &P = a.peers;
+    const bool any = __syncthreads_or(pushed);
+    if (threadIdx.x == 0) {
+        if (any) __threadfence_system(); else __threadfence();
+        const unsigned int t = atomicAdd(&a.sync->arrive_h, 1u);
+        const int buf = kPcgFlagH + (int)(hseq & 1ull);
+        if (t == gridDim.x - 1) {
+            a.sync->arrive_h = 0u;
+            __threadfence_system();
+            for (int sgm = 0; sgm < a.halo.n_send; ++sgm) st_release_sys(p2p_flag(P, a.halo.send_peer[sgm], buf, P.rank), hseq);
+            st_release_gpu(&a.sync->gen_h, hseq);
+        }
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(&a.sync->gen_h) < hseq)
+            if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 2; break; }
+        for (int sgm = 0; sgm < a.halo.n_recv; ++sgm) {
+            const unsigned long long *f = p2p_flag(P, P.rank, buf, a.halo.recv_peer[sgm]);
+            while (ld_acquire_sys(f) < hseq)
+                if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 3; break; }
+        }
+        __threadfence();   // as cooperative-groups' grid sync: what other SMs / GPUs wrote is now visible to plain loads
+    }
+    __syncthreads();
+}
+
+// Barrier R + all-reduce.  On entry every CTA has written its `nparts` partial sums (partials[q * grid + cta])
+// and the cluster warps their entries of a.payload[4 ..).  On return out[0 .. 3] hold the global sums of the
+// partial arrays, and the slots of parity (rseq & 1) the cluster entries of every rank.  K = payload length.
+__device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned long long rseq, int nparts, int K,
+                                                   double *out, double *sh) {
+    const P2pPeers &P = a.peers;
+    __shared__ bool s_last;
+    __shared__ int s_err;
+    __shared__ double s_loc[4];
+    const int buf = (int)(rseq & 1ull);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&a.sync->arrive_r, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const int G = (int)gridDim.x;
+        for (int q = 0; q < 4; ++q) {
+            double acc = 0.0;
+            if (q < nparts)
+                for (int i = threadIdx.x; i < G; i += blockDim.x) acc += __ldcg(a.partials + (size_t)q * G + i);
+            acc = block_sum(acc, sh);
+            if (threadIdx.x == 0) s_loc[q] = acc;
+        }
+        __syncthreads();
+        for (int q = 0; q < P.world; ++q) {
+            double *slot = pcg_slot(P, q, buf, P.rank);
+            for (int j = threadIdx.x; j < K; j += blockDim.x) slot[j] = j < 4 ? s_loc[j] : __ldcg(a.payload + j);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { a.sync->arrive_r = 0u; __threadfence_system(); }
+        __syncthreads();
+        for (int q = threadIdx.x; q < P.world; q += blockDim.x) st_release_sys(p2p_flag(P, q, kPcgFlagR + buf, P.rank), rseq);
+    }
+    for (int q = threadIdx.x; q < P.world; q += blockDim.x) {
+        const unsigned long long *f = p2p_flag(P, P.rank, kPcgFlagR + buf, q);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < rseq)
+            if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 4; break; }
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) out[threadIdx.x] = pcg_reduced(P, buf, threadIdx.x);
+    if (threadIdx.x == 0) s_err = *reinterpret_cast<volatile int *>(&a.sc->pad);   // a wait timed out somewhere on this GPU
+    __syncthreads();
+    return s_err != 0;
+}
+
+// sum over a row of A times g, lanes striding the row (fixed order: deterministic); result in every lane
+__device__ __forceinline__ double pcg_warp_row_dot(const PcgArgs &a, const double *g, int row, int lane) {
+    double s = 0.0;
+    for (int k = __ldg(a.row_ptr + row) + lane, e = __ldg(a.row_ptr + row + 1); k < e; k += 32)
+        s += __ldg(a.val + k) * g[__ldg(a.col + k)];
+    return warp_sum(s);
+}
+
+// SpMV over the own tiles: y = A g (MODE 1, returns the CTA's share of y.g) or y = b - A g (MODE 2).
+// Same tile algorithm as spmv_tile_kernel: the tile's val/col streamed coalesced, eight per thread in flight,
+// products parked in shared memory, every row added in CSR order.
+template <int MODE>
+__device__ __forceinline__ double pcg_spmv_tiles(const PcgArgs &a, const double *g, double *y, double *prod) {
+    double local = 0.0;
+    for (int t = a.t0 + (int)blockIdx.x; t < a.t1; t += (int)gridDim.x) {
+        const int4 ti = __ldg(a.tile_info + t);
+        const int r0 = ti.x, r1 = ti.y;
+        if (r0 < r1) {
+            const int k0 = ti.z, k1 = ti.w;
+            const int ka = k0 & ~1;
+            int my_r = r0 + threadIdx.x, ra = 0, rb = 0;
+            if (my_r < r1) { ra = __ldg(a.row_ptr + my_r); rb = __ldg(a.row_ptr + my_r + 1); }
+            if (k1 - ka <= kSpmvCap) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double v[4];
+                    int c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
+                        const bool ok = k < k1;
+                        v[u] = ok ? __ldcs(a.val + k) : 0.0;
+                        c[u] = ok ? __ldcs(a.col + k) : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
+                        if (k < k1) prod[k - ka] = v[u] * g[c[u]];
+                    }
+                }
+                __syncthreads();
+                for (int r = my_r; r < r1; r += kSpmvThreads) {
+                    if (r != my_r) { ra = __ldg(a.row_ptr + r); rb = __ldg(a.row_ptr + r + 1); }
+                    double s = 0.0;
+#pragma unroll 4
+                    for (int k = ra - ka; k < rb - ka; ++k) s += prod[k];
+                    if (MODE == 2) s = __ldg(a.b + r) - s;
+                    y[r] = s;
+                    if (MODE == 1) local += g[r] * s;
+                }
+            } else {  // rows too long for the staging buffer
+                for (int r = my_r; r < r1; r += kSpmvThreads) {
+                    double s = 0.0;
+                    for (int k = __ldg(a.row_ptr + r); k < __ldg(a.row_ptr + r + 1); ++k) s += __ldg(a.val + k) * g[__ldg(a.col + k)];
+                    if (MODE == 2) s = __ldg(a.b + r) - s;
+                    y[r] = s;
+                    if (MODE == 1) local += g[r] * s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    return local;
+}
+
+// cluster rows: payload[4 + off + s] = sum over the members of cluster s this rank owns of f(row), with
+// f = (A g)_row (MODE 1) or b_row - (A g)_row (MODE 2, and b_row into the second array).  One warp per cluster.
+template <int MODE>
+__device__ __forceinline__ void pcg_cluster_rows(const PcgArgs &a, const double *g) {
+    const int n = a.n_cl;
+    if (n <= 0) return;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int s = (int)blockIdx.x * wpb + (threadIdx.x >> 5); s < n; s += (int)gridDim.x * wpb) {
+        double acc = 0.0, accb = 0.0;
+        if (__ldg(a.P.seg_start + s) == s) {
+            const int len = __ldg(a.P.seg_len + s);
+            for (int k = 0; k < len; ++k) {
+                const int row = __ldg(a.P.mem_row + s + k);
+                if (row < a.ra || row >= a.rb) continue;
+                const double d = pcg_warp_row_dot(a, g, row, lane);
+                if (MODE == 2) { const double bv = __ldg(a.b + row); acc += bv - d; accb += bv; }
+                else acc += d;
+            }
+        }
+        if (lane == 0) {
+            a.payload[4 + s] = acc;
+            if (MODE == 2) a.payload[4 + n + s] = accb;
+        }
+    }
+}
+
+// MINB = CTAs per SM the register budget allows: 5 (48 registers) on an SM of its own, 6 (40 registers, a few
+// spilled scalars) when the overlapped pairwise kernel holds part of the register file
+template <int MINB>
+__global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(const PcgArgs a) {
+    __shared__ __align__(16) double prod[kSpmvCap];
+    __shared__ double red[32];
+    __shared__ double s_out[4];
+    const P2pPeers &P = a.peers;
+    const int G = (int)gridDim.x, B = (int)blockDim.x, cta = (int)blockIdx.x, tid = (int)threadIdx.x;
+    const int n = a.n_cl;
+    double *g = reinterpret_cast<double *>(P.base[P.rank]);   // u: own rows + the neighbours' boundary rows
+    unsigned long long rseq = a.rseq0, hseq = a.hseq0;
+    const bool clustered = a.P.pos != nullptr && n > 0;
+    long long tp = 0, prof[5] = {0, 0, 0, 0, 0};
+    const bool do_prof = a.prof != nullptr && cta == 0 && tid == 0;
+    if (do_prof) tp = pcg_now();
+#define PCG_PROF(slot) do { if (do_prof) { const long long now__ = pcg_now(); prof[slot] += now__ - tp; tp = now__; } } while (0)
+
+    // ---- init 0: u := x over the own rows (the SpMV gathers from the window), boundary rows to the neighbours
+    {
+        bool pushed = false;
+        for (int i = a.ra + cta * B + tid; i < a.rb; i += G * B) {
+            const double v = a.x[i];
+            g[i] = v;
+            pushed |= pcg_push(a.halo, P, i, v);
+        }
+        pcg_barrier_halo(a, ++hseq, pushed);
+    }
+    // ---- init 1: r = b - A x; cluster sums of r and of b
+    pcg_spmv_tiles<2>(a, g, a.r, prod);
+    if (clustered) pcg_cluster_rows<2>(a, g);
+    pcg_barrier_reduce(a, ++rseq, 0, 4 + 2 * n, s_out, red);
+    // ---- init 2: u = M^-1 r (into the window), gamma and b.M^-1 b partials, recurrence state
+    {
+        const int rb_ = (int)(rseq & 1ull);
+        double lg = 0.0, lbb = 0.0;
+        bool pushed = false;
+        for (int i = a.ra + cta * B + tid; i < a.rb; i += G * B) {
+            const double ri = a.r[i], bi = __ldg(a.b + i), di = __ldg(a.dinv + i);
+            double un = ri * di, zb = bi * di;
+            const int sp = clustered ? __ldg(a.P.pos + i) : -1;
+            if (sp >= 0) {
+                const int st = __ldg(a.P.seg_start + sp);
+                const double we = __ldg(a.P.w + st);
+                un += we * pcg_reduced(P, rb_, 4 + st);
+                zb += we * pcg_reduced(P, rb_, 4 + n + st);
+            }
+            g[i] = un;
+            pushed |= pcg_push(a.halo, P, i, un);
+            lg += ri * un;
+            lbb += bi * zb;
+        }
+        for (int s = cta * B + tid; s < n; s += G * B)
+            if (__ldg(a.P.seg_start + s) == s) { a.cr[s] = pcg_reduced(P, rb_, 4 + s); a.cs[s] = 0.0; }
+        lg = block_sum(lg, red);
+        __syncthreads();
+        lbb = block_sum(lbb, red);
+        if (tid == 0) { a.partials[cta] = lg; a.partials[2 * (size_t)G + cta] = lbb; }
+        pcg_barrier_halo(a, ++hseq, pushed);
+    }
+    // ---- init 3: w = A u; delta partial; cluster sums of w
+    {
+        double ld = pcg_spmv_tiles<1>(a, g, a.w, prod);
+        if (clustered) pcg_cluster_rows<1>(a, g);
+        ld = block_sum(ld, red);
+        if (tid == 0) a.partials[(size_t)G + cta] = ld;
+        pcg_barrier_reduce(a, ++rseq, 3, 4 + n, s_out, red);
+    }
+    double gamma = s_out[0], delta = s_out[1];
+    const double bb = s_out[2];
+    const double stop = a.tol * a.tol * (bb > 0.0 ? bb : gamma);
+    double alpha = gamma / delta, beta = 0.0;
+    int iters = 0, par = 0;
+    bool done = gamma <= stop || !(gamma == gamma);
+    bool err = false;
+    PCG_PROF(0);
+
+    while (!done && !err && iters < a.max_iter) {
+        // ---- V: p, s, x, r, u over the own rows; gamma partial
+        {
+            const int rb_ = (int)(rseq & 1ull);
+            const double *cs_old = a.cs + (size_t)par * n, *cr_old = a.cr + (size_t)par * n;
+            double *cs_new = a.cs + (size_t)(par ^ 1) * n, *cr_new = a.cr + (size_t)(par ^ 1) * n;
+            const bool first = iters == 0;
+            double lg = 0.0;
+            bool pushed = false;
+            for (int i = a.ra + cta * B + tid; i < a.rb; i += G * B) {
+                // every load before the first store: the vectors may alias as far as the compiler knows, and a
+                // load behind a store would wait for it (three dependent round trips per pass instead of one)
+                const double ui = g[i], wi = a.w[i], xi = a.x[i], ro = a.r[i], di = __ldg(a.dinv + i);
+                const int sp = clustered ? __ldg(a.P.pos + i) : -1;
+                double pi = ui, si = wi;
+                if (!first) { pi += beta * a.p[i]; si += beta * a.s[i]; }
+                const double ri = ro - alpha * si;
+                a.p[i] = pi;
+                a.s[i] = si;
+                a.x[i] = xi + alpha * pi;
+                a.r[i] = ri;
+                double un = ri * di;
+                if (sp >= 0) {
+                    const int st = __ldg(a.P.seg_start + sp);
+                    const double csn = pcg_reduced(P, rb_, 4 + st) + beta * cs_old[st];
+                    un += __ldg(a.P.w + st) * (cr_old[st] - alpha * csn);
+                }
+                g[i] = un;
+                pushed |= pcg_push(a.halo, P, i, un);
+                lg += ri * un;
+            }
+            for (int s = cta * B + tid; s < n; s += G * B)
+                if (__ldg(a.P.seg_start + s) == s) {
+                    const double csn = pcg_reduced(P, rb_, 4 + s) + beta * cs_old[s];
+                    cs_new[s] = csn;
+                    cr_new[s] = cr_old[s] - alpha * csn;
+                }
+            par ^= 1;
+            lg = block_sum(lg, red);
+            if (tid == 0) a.partials[cta] = lg;
+            PCG_PROF(1);
+            pcg_barrier_halo(a, ++hseq, pushed);
+            PCG_PROF(2);
+        }
+        // ---- S: w = A u; delta partial; cluster sums of w; the one reduction of the iteration
+        {
+            double ld = pcg_spmv_tiles<1>(a, g, a.w, prod);
+            if (clustered) pcg_cluster_rows<1>(a, g);
+            ld = block_sum(ld, red);
+            if (tid == 0) a.partials[(size_t)G + cta] = ld;
+            PCG_PROF(3);
+            err = pcg_barrier_reduce(a, ++rseq, 2, 4 + n, s_out, red);
+            PCG_PROF(4);
+        }
+        const double gamma_new = s_out[0];
+        delta = s_out[1];
+        beta = gamma_new / gamma;
+        alpha = gamma_new / (delta - beta * gamma_new / alpha);
+        gamma = gamma_new;
+        ++iters;
+        done = gamma <= stop || !(gamma == gamma);
+    }
+    if (cta == 0 && tid == 0) {
+        CgScalars *sc = a.sc;
+        sc->rz = gamma; sc->bb = bb; sc->stop = stop; sc->iters = iters; sc->max_iter = a.max_iter;
+        sc->done = done ? 1 : 0;
+        sc->alpha = alpha; sc->beta = beta;
+        sc->rseq_end = rseq; sc->hseq_end = hseq;
+        if (a.prof) {
+            for (int q = 0; q < 5; ++q) a.prof[q] += prof[q];
+            a.prof[5] += iters;
+            a.prof[6] += 1;
+        }
+    }
+#undef PCG_PROF
+}
+

@@ -20,8 +20,6 @@
 #define DKMC_CARVEOUT_MAXSHARED 1
 #include "common.cuh"
 #include "scan.cuh"
-#include "spmv_tma.cuh"
-#include "spmv_win.cuh"
 
 namespace dkmc {
 
@@ -38,15 +36,10 @@ static int g_flags = [] { const char *e = getenv("DKMC_FLAGS"); return e ? atoi(
 
 struct CgScalars {
     double rz, rz_new, pAp, alpha, beta, bb, stop, resnorm2, bnorm2;
-    int done, iters, max_iter, pad;
+    int done, iters, max_iter, pad;     // pad != 0: a cross-CTA / cross-GPU wait timed out (error)
     unsigned int cnt_a, cnt_b, cnt_c, cnt_d;
+    unsigned long long rseq_end, hseq_end;   // persistent PCG: sequence numbers reached (reductions, halo exchanges)
 };
-
-// Packed CSR of K for the CG's SpMV: K has two distinct off-diagonal values (-high_G, -low_G), so the
-// assembly also writes, per non-zero, the column with the choice in bit 31 (and bit 30 on the diagonal,
-// whose value lives in a per-row array).  The SpMV then streams 4 bytes per non-zero instead of 12
-// and forms the very same products, hence bit-identical results.
-constexpr int kPackHigh = (int)0x80000000u, kPackDiag = 0x40000000, kPackMask = 0x3fffffff;
 
 // ---------------------------------------------------------------- site class + assembly
 __global__ void site_class_kernel(int N, const int *__restrict__ element, const int *__restrict__ charge,
@@ -75,9 +68,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(
     const unsigned char *__restrict__ cls, const int *__restrict__ row_ptr, const int *__restrict__ col,
     const int *__restrict__ lrp, const int *__restrict__ lcol, const int *__restrict__ rrp,
     const int *__restrict__ rcol, double *__restrict__ val, double *__restrict__ rhs,
-    double *__restrict__ dinv, const unsigned short *__restrict__ code_base, const int *__restrict__ code_pos,
-    const int *__restrict__ diag_pos, unsigned char *__restrict__ blobs, int *__restrict__ pcol,
-    double *__restrict__ pdiag) {
+    double *__restrict__ dinv) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     const unsigned char ci = cls[r + NL];
@@ -89,17 +80,12 @@ __global__ void __launch_bounds__(128) assemble_kernel(
         ksub = __dadd_rn(ksub, __dmul_rn(-G, VL));
     }
     int dpos = -1;
-    // window-staged format (spmv_win.cuh): this row's codes and diagonal slot inside its tile's blob
-    const int row_begin = row_ptr[r];
-    unsigned short *code = blobs ? reinterpret_cast<unsigned short *>(blobs) + code_pos[r] - row_begin : nullptr;
-    for (int p = row_begin; p < row_ptr[r + 1]; ++p) {
+    for (int p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
         int c = col[p];
         if (c == r) { dpos = p; continue; }
         const unsigned char cj = cls[c + NL];
         double G = conductance(ci, cj, high_G, low_G, rule);
         val[p] = -G;
-        if (pcol) pcol[p] = c | (is_high(ci, cj, rule) ? kPackHigh : 0);           // packed CSR: column | high_G bit
-        if (code) code[p] = code_base[p] | (is_high(ci, cj, rule) ? 0x4000 : 0);  // window-staged format: high_G bit
         diag = __dadd_rn(diag, G);
     }
     for (int p = rrp[r]; p < rrp[r + 1]; ++p) {
@@ -107,13 +93,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(
         diag = __dadd_rn(diag, G);
         ksub = __dadd_rn(ksub, __dmul_rn(-G, VR));
     }
-    if (dpos >= 0) {
-        val[dpos] = diag;
-        if (pcol) pcol[dpos] = r | kPackDiag;
-        if (code) code[dpos] = code_base[dpos];
-    }
-    if (pdiag) pdiag[r] = diag;
-    if (blobs) reinterpret_cast<double *>(blobs)[diag_pos[r]] = diag;
+    if (dpos >= 0) val[dpos] = diag;
     rhs[r] = -ksub;  // D*phi = -Ksub (potential_solver.cpp:379,396)
     if (dinv) dinv[r] = 1.0 / diag;
 }
@@ -139,17 +119,15 @@ __global__ void tile_rows_kernel(int m, int num_tiles, const int *__restrict__ r
 
 // y = A x over one nnz tile per block.  MODE 0: y only.  MODE 1: also dot(w, y) -> *dot_out.
 // MODE 2: y = b - A x (residual) and rr = sum (y^2 * dinv) -> *dot_out.
-// Phase 1 streams the tile's val/col with 16-byte loads, all 8 elements of a thread in flight at
-// once (one DRAM round trip per tile), gathers x through the read-only path and parks the
-// products in shared memory; phase 2 adds each row's products in CSR order.
-// PACKED: `col` holds the packed columns, `val` the per-row diagonal, (m_high, m_low) the two
-// off-diagonal values.
-template <int MODE, bool PACKED = false>
+// Phase 1 streams the tile's val/col with all 8 elements of a thread in flight at once (one DRAM round
+// trip per tile), gathers x through the read-only path and parks the products in shared memory;
+// phase 2 adds each row's products in CSR order.
+template <int MODE>
 __global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_kernel(
     int num_tiles, int nnz, const int *__restrict__ row_ptr, const int *__restrict__ col, const double *__restrict__ val,
     const double *__restrict__ x, double *__restrict__ y, const int4 *__restrict__ tile_info,
     const double *__restrict__ w, const double *__restrict__ dinv, double *partials, unsigned int *counter,
-    double *dot_out, const int *done_flag, int flags, double m_high = 0.0, double m_low = 0.0) {
+    double *dot_out, const int *done_flag, int flags) {
     __shared__ __align__(16) double prod[kSpmvCap];
     __shared__ double red[32];
     if (done_flag && *done_flag) return;
@@ -160,7 +138,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_ker
         const int r0 = ti.x, r1 = ti.y;
         if (r0 < r1) {
             const int k0 = ti.z, k1 = ti.w;
-            const int ka = k0 & ~1;  // even start: 16-byte aligned double2 / 8-byte aligned int2
+            const int ka = k0 & ~1;
             // row bounds of this thread's first row, requested before the big loads
             int my_r = r0 + threadIdx.x, ra = 0, rb = 0;
             if (my_r < r1) { ra = row_ptr[my_r]; rb = row_ptr[my_r + 1]; }
@@ -174,9 +152,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_ker
                     for (int u = 0; u < 4; ++u) {
                         int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
                         bool ok = k < k1;
-                        if (PACKED) {
-                            c[u] = ok ? __ldcs(col + k) : 0;
-                        } else if (flags & 1) {  // keep the matrix in L2 across CG iterations
+                        if (flags & 1) {  // keep the matrix in L2 across CG iterations
                             v[u] = ok ? __ldg(val + k) : 0.0;
                             c[u] = ok ? __ldg(col + k) : 0;
                         } else {
@@ -187,14 +163,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_ker
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
-                        if (PACKED) {
-                            const int cc = c[u] & kPackMask;
-                            const double xv = __ldg(x + cc);
-                            const double vv = (c[u] & kPackDiag) ? __ldg(val + cc) : (c[u] < 0 ? m_high : m_low);
-                            if (k < k1) prod[k - ka] = vv * xv;
-                        } else if (k < k1) {
-                            prod[k - ka] = v[u] * __ldg(x + c[u]);
-                        }
+                        if (k < k1) prod[k - ka] = v[u] * __ldg(x + c[u]);
                     }
                 }
                 __syncthreads();
@@ -211,14 +180,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MODE == 0 ? 8 : 6) spmv_tile_ker
             } else {  // rows too long for the staging buffer: direct path
                 for (int r = my_r; r < r1; r += kSpmvThreads) {
                     double s = 0.0;
-                    for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
-                        if (PACKED) {
-                            const int pc = col[k], cc = pc & kPackMask;
-                            s += ((pc & kPackDiag) ? val[cc] : (pc < 0 ? m_high : m_low)) * __ldg(x + cc);
-                        } else {
-                            s += val[k] * __ldg(x + col[k]);
-                        }
-                    }
+                    for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) s += val[k] * __ldg(x + col[k]);
                     if (MODE == 2) { s = w[r] - s; local += s * s * dinv[r]; }
                     y[r] = s;
                     if (MODE == 1) local += w[r] * s;
@@ -676,6 +638,7 @@ struct CgWork {
     const int4 *tile_row;
     int num_tiles;
     Precond P;
+    int n_cl;   // clustered rows (length of the sorted member list), host copy
 };
 
 static int cg_workspace(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, CgWork *w) {
@@ -694,6 +657,7 @@ static int cg_workspace(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, CgW
     if ((rc = ensure<CgScalars>(ctx, S_SCALARS, 4, &w->sc))) return rc;
     if (fresh) DKMC_CUDA(cudaMemsetAsync(w->sc, 0, 4 * sizeof(CgScalars), ctx->stream));
     w->P = Precond{w->dinv, nullptr, nullptr, nullptr, nullptr, nullptr};
+    w->n_cl = 0;
     return DKMC_OK;
 }
 
@@ -724,158 +688,49 @@ static int build_clusters(dkmc_ctx *ctx, int m, int NL, const unsigned char *cls
                 seg_start, seg_len);
     DKMC_LAUNCH(ctx, cluster_weight_kernel, 64, 128, 0, total, pos, seg_start, seg_len, mem_row, d_row_ptr, d_col, d_val, wts);
     w->P = Precond{w->dinv, pos, seg_start, seg_len, mem_row, wts};
-    return DKMC_OK;
-}
-
-// Builds (once per sparsity pattern) the window-staged format of spmv_win.cuh.
-static int get_win_format(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const int4 *tile_info,
-                          int num_tiles) {
-    WinFormat &w = ctx->win;
-    if (!ctx->use_window_spmv) return DKMC_OK;
-    if (w.row_ptr == d_row_ptr && w.col == d_col && w.m == m && w.nnz == nnz) return DKMC_OK;
+    // the persistent PCG sizes its reduction payload by the number of clustered rows
+    DKMC_CUDA(cudaMemcpyAsync(&w->n_cl, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
-    free_win_format(ctx);
-    // blob sizes follow from the tile extents alone: lay them out on the host
-    std::vector<int4> ti((size_t)num_tiles), plan((size_t)num_tiles);
-    DKMC_CUDA(cudaMemcpy(ti.data(), tile_info, (size_t)num_tiles * sizeof(int4), cudaMemcpyDeviceToHost));
-    size_t off = 0;
-    for (int t = 0; t < num_tiles; ++t) {
-        const int rows = ti[t].y - ti[t].x, n = ti[t].w - ti[t].z;
-        const bool fits = n <= kWinMaxTileNnz && rows <= kWinMaxTileNnz && n >= 0 && rows >= 0;
-        const WinBlob B = win_blob(fits ? rows : 0, fits ? n : 0);
-        plan[t] = make_int4((int)(off / 128), B.bytes, 0, 0);
-        off += (size_t)B.bytes;
-    }
-    if (off / 2 >= 0x7fffffffull) {  // row positions are 32-bit halfword indices
-        w.row_ptr = d_row_ptr; w.col = d_col; w.m = m; w.nnz = nnz; w.num_tiles = num_tiles; w.ok = false;
-        return DKMC_OK;
-    }
-    w.blob_bytes = off;
-    DKMC_CUDA(cudaMalloc(&w.blobs, off + 256));
-    DKMC_CUDA(cudaMalloc(&w.plan, (size_t)num_tiles * sizeof(int4)));
-    DKMC_CUDA(cudaMalloc(&w.code_base, ((size_t)nnz + 32) * sizeof(unsigned short)));
-    DKMC_CUDA(cudaMalloc(&w.code_pos, ((size_t)m + 8) * sizeof(int)));
-    DKMC_CUDA(cudaMalloc(&w.diag_pos, ((size_t)m + 8) * sizeof(int)));
-    DKMC_CUDA(cudaMemsetAsync(w.blobs, 0, off + 256, ctx->stream));
-    DKMC_CUDA(cudaMemcpyAsync(w.plan, plan.data(), (size_t)num_tiles * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
-    int *flags;  // fail bits | max staged tile
-    int rc;
-    if ((rc = ensure<int>(ctx, S_SEL_OUT, 4, &flags))) return rc;
-    DKMC_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
-    DKMC_LAUNCH(ctx, win_build_kernel, num_tiles, 256, 0, m, num_tiles, d_row_ptr, d_col, tile_info,
-                static_cast<int4 *>(w.plan), w.blobs, w.code_base, w.code_pos, w.diag_pos, flags, flags + 1);
-    int h[2] = {0, 0};
-    DKMC_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));  // also keeps `plan` alive until the copy is done
-    w.row_ptr = d_row_ptr; w.col = d_col; w.m = m; w.nnz = nnz; w.num_tiles = num_tiles;
-    w.fail_bits = h[0]; w.max_chunk = h[1];
-    w.ok = (h[0] == 0);
-    w.val_tag = nullptr;
-    if (getenv("DKMC_VERBOSE"))
-        fprintf(stderr, "dkmc: window-staged SpMV format: %d tiles, %.1f MB of blobs (%.2f bytes per non-zero), largest staged "
-                "tile %d bytes, fail bits %d -> %s\n", num_tiles, off / 1e6, (double)off / nnz, h[1], h[0],
-                w.ok ? "enabled" : "CSR kernels");
     return DKMC_OK;
 }
 
-// SpMV over `ntiles` tiles starting at `tile_info`.  Three kernels with bit-identical y:
-//   * register-staged CSR (spmv_tile_kernel): the default.  Measured at 1 M sites: 67 us alone (75 % of
-//     the measured HBM peak), CG iteration 111 us;
-//   * TMA-fed CSR (spmv_tma.cuh), DKMC_FLAGS bit 4: 87 us alone, CG iteration 128 us — its three
-//     74 KB rings per SM leave the x gathers almost no L1;
-//   * window-staged (spmv_win.cuh), opt-in through dkmc_ctx_set_window_spmv: 4x fewer DRAM bytes,
-//     73-86 us, bound by shared-memory gathers and instruction issue.
-// x_readable = number of doubles that may be read from d_x (window-staged kernel only).
+// SpMV over `ntiles` tiles starting at `tile_info` (register-staged CSR tiles).  Measured at 1 M sites: 67 us
+// alone (75 % of the measured HBM peak).  Round 1 also carried a TMA-fed, a packed (4 B per non-zero) and a
+// window-staged (2.6 B per non-zero) variant, all bit-identical and all slower inside the CG — the kernel is
+// bound by the 26 M gathers of x, not by what it streams; they were removed in round 2.
 template <int MODE>
 static int launch_spmv(dkmc_ctx *ctx, int ntiles, int m, int nnz, const int *d_row_ptr, const int *d_col,
                        const double *d_val, const double *d_x, double *d_y, const int4 *tile_info, const double *w,
                        const double *dinv, double *partials, unsigned int *counter, double *dot_out,
-                       const int *done_flag, int x_readable = 0) {
+                       const int *done_flag) {
+    (void)m;
     if (ntiles <= 0) return DKMC_OK;
-    const WinFormat &wf = ctx->win;
-    if (ctx->use_window_spmv && wf.ok && wf.row_ptr == d_row_ptr && wf.val_tag == d_val && d_val != nullptr &&
-        (reinterpret_cast<uintptr_t>(d_x) & 63) == 0 && x_readable >= ((m + 7) & ~7) && (MODE != 1 || w == d_x)) {
-        static bool configured = false;
-        if (!configured) {
-            DKMC_CUDA(cudaFuncSetAttribute(spmv_win_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWinSmemBytes));
-            configured = true;
-        }
-        const int t0 = (int)(tile_info - reinterpret_cast<const int4 *>(ctx->tiling.d_tile_row));
-        WinMatrix A;
-        A.blobs = wf.blobs;
-        A.plan = static_cast<const int4 *>(wf.plan) + t0;
-        A.m_high = wf.m_high; A.m_low = wf.m_low; A.num_tiles = ntiles;
-        static const int dbg = [] { const char *e = getenv("DKMC_WIN_DBG"); return e ? atoi(e) : 0; }();
-        // experiment: DKMC_WIN_CFG="ctas_per_sm,threads,loaders"
-        static int cfg[3] = {1, kWinThreads, kWinLoaders};
-        static bool cfg_read = false;
-        if (!cfg_read) { const char *e = getenv("DKMC_WIN_CFG"); if (e) sscanf(e, "%d,%d,%d", &cfg[0], &cfg[1], &cfg[2]); cfg_read = true; }
-        int ring = ((kWinRingBytes / cfg[0]) / 128) * 128;
-        if (ring < wf.max_chunk) ring = wf.max_chunk;
-        const size_t smem = (size_t)ring + (kWinSmemBytes - kWinRingBytes);
-        int grid = ctx->num_sms * cfg[0];
-        if (grid > ntiles) grid = ntiles;
-        long long *prof = nullptr;
-        if (dbg & 16) {  // per-role wait/total cycle sums (see tools/spmv_experiment.py)
-            int rc;
-            if ((rc = ensure<long long>(ctx, S_SEL_OUT, 8, &prof))) return rc;
-            DKMC_CUDA(cudaMemsetAsync(prof, 0, 8 * sizeof(long long), ctx->stream));
-        }
-        DKMC_LAUNCH(ctx, spmv_win_kernel<MODE>, grid, cfg[1], smem, A, d_x, d_y, w, dinv, partials, counter,
-                    dot_out, done_flag, dbg, ring, cfg[2], prof);
-        if (dbg & 16) {
-            long long h[8];
-            DKMC_CUDA(cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-            DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
-            static int printed = 0;
-            if (printed++ < 2) {
-                const double nc = grid, nl = (double)grid * cfg[2], nco = (double)grid * (cfg[1] / 32 - 1 - cfg[2]);
-                fprintf(stderr, "win prof (kcycles per warp): producer wait %.1f of %.1f | loader wait %.1f of %.1f | consumer wait %.1f of %.1f\n",
-                        h[0] / nc / 1e3, h[1] / nc / 1e3, h[2] / nl / 1e3, h[3] / nl / 1e3, h[4] / nco / 1e3, h[5] / nco / 1e3);
-            }
-        }
-        return DKMC_OK;
-    }
-    const PackedCsr &pk = ctx->packed;
-    if (ctx->use_packed_spmv && pk.pcol && pk.row_ptr == d_row_ptr && pk.val_tag == d_val && d_val != nullptr) {
-        int grid = ctx->num_sms * 6;
-        if (MODE == 0 || grid > ntiles) grid = ntiles;
-        DKMC_LAUNCH(ctx, (spmv_tile_kernel<MODE, true>), grid, kSpmvThreads, 0, ntiles, nnz, d_row_ptr, pk.pcol, pk.diag, d_x,
-                    d_y, tile_info, w, dinv, partials, counter, dot_out, done_flag, g_flags, pk.m_high, pk.m_low);
-        return DKMC_OK;
-    }
-    const bool aligned = ((reinterpret_cast<uintptr_t>(d_val) | reinterpret_cast<uintptr_t>(d_col)) & 15) == 0;
-    if (aligned && (g_flags & 16)) {
-        static bool configured = false;
-        if (!configured) {
-            DKMC_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
-            configured = true;
-        }
-        // three CTAs (3 x 74 KB of stages) fill an SM; two while the pairwise kernel shares it
-        static const int cps_alone = [] { const char *e = getenv("DKMC_SPMV_CPS"); return e ? atoi(e) : 3; }();
-        int grid = ctx->num_sms * (ctx->pw_pending.active ? 2 : cps_alone);
-        if (grid > ntiles) grid = ntiles;
-        DKMC_LAUNCH(ctx, spmv_tma_kernel<MODE>, grid, kTmaThreads, kTmaSmemBytes, ntiles, nnz, d_row_ptr, d_col, d_val, d_x,
-                    d_y, tile_info, w, dinv, partials, counter, dot_out, done_flag);
-    } else {
-        int grid = ctx->num_sms * 6;
-        if (MODE == 0 || grid > ntiles) grid = ntiles;  // no dot to finish: one tile per CTA
-        DKMC_LAUNCH(ctx, spmv_tile_kernel<MODE>, grid, kSpmvThreads, 0, ntiles, nnz, d_row_ptr, d_col, d_val, d_x, d_y,
-                    tile_info, w, dinv, partials, counter, dot_out, done_flag, g_flags);
-    }
+    int grid = ctx->num_sms * 6;
+    if (MODE == 0 || grid > ntiles) grid = ntiles;  // no dot to finish: one tile per CTA
+    DKMC_LAUNCH(ctx, spmv_tile_kernel<MODE>, grid, kSpmvThreads, 0, ntiles, nnz, d_row_ptr, d_col, d_val, d_x, d_y,
+                tile_info, w, dinv, partials, counter, dot_out, done_flag, g_flags);
     return DKMC_OK;
 }
+
+// the persistent-kernel PCG (pcg_persistent.cuh) on one GPU; defined below, after the peer-window plumbing
+static bool use_persistent_pcg(const dkmc_ctx *ctx);
+static int run_pcg_persistent_single(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
+                                     const double *d_val, const double *d_b, double *d_x, const CgWork &w, double tol,
+                                     int max_iter, int *iters_out, int *converged, double *bb_out);
 
 // Preconditioned CG on A x = b starting from x (in/out).  w.P must be set.
 static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                    const double *d_b, double *d_x, const CgWork &w, double tol, int max_iter, int check_every,
-                   int *iters_out, int *converged, double *bb_out, int x_readable) {
+                   int *iters_out, int *converged, double *bb_out) {
+    if (use_persistent_pcg(ctx))
+        return run_pcg_persistent_single(ctx, m, nnz, d_row_ptr, d_col, d_val, d_b, d_x, w, tol, max_iter, iters_out, converged,
+                                         bb_out);
+    // legacy path (DKMC_LEGACY_CG=1): three launches per iteration, the host polls a flag every `check_every`
     const int vg = vec_grid(ctx, m);
-    const int own = m + 32;  // the arena's buffers carry at least 256 bytes of slack
     // r = b - A x, then z/p/rz/bb
     int rc0;
     if ((rc0 = launch_spmv<2>(ctx, w.num_tiles, m, nnz, d_row_ptr, d_col, d_val, d_x, w.r[0], w.tile_row, d_b, w.dinv,
-                              w.partials, &w.sc->cnt_c, &w.sc->resnorm2, nullptr, x_readable))) return rc0;
+                              w.partials, &w.sc->cnt_c, &w.sc->resnorm2, nullptr))) return rc0;
     DKMC_LAUNCH(ctx, cg_init_kernel, vg, kVecThreads, 0, m, w.r[0], d_b, w.P, w.p, tol, max_iter, w.partials, w.sc);
     CgScalars h;
     memset(&h, 0, sizeof(h));
@@ -885,7 +740,7 @@ static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const in
     while (true) {
         for (int k = 0; k < check_every; ++k) {
             if ((rc0 = launch_spmv<1>(ctx, w.num_tiles, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap, w.tile_row, w.p, nullptr,
-                                      w.partials, &w.sc->cnt_c, &w.sc->pAp, &w.sc->done, own))) return rc0;
+                                      w.partials, &w.sc->cnt_c, &w.sc->pAp, &w.sc->done))) return rc0;
             DKMC_LAUNCH(ctx, cg_update_kernel, vg, kVecThreads, 0, m, d_x, w.r[cur], w.r[cur ^ 1], w.p, w.Ap, w.P,
                         w.partials, w.sc, g_flags);
             cur ^= 1;
@@ -957,10 +812,10 @@ static int true_residual(dkmc_ctx *ctx, int m, const int *d_row_ptr, const int *
 
 static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
                          const double *d_val, const double *d_rhs, double *d_x, CgWork &w,
-                         const dkmc_solver_opts &o, dkmc_solve_info *info, int x_readable) {
+                         const dkmc_solver_opts &o, dkmc_solve_info *info) {
     int iters = 0, conv = 0, total = 0, rc;
     double bb0 = 0.0, rel = 0.0, est = 0.0;
-    if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o.rel_tol, o.max_iter, o.check_every, &iters, &conv, &bb0, x_readable))) return rc;
+    if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o.rel_tol, o.max_iter, o.check_every, &iters, &conv, &bb0))) return rc;
     total += iters;
     bool all_conv = conv != 0;
     const int vg = vec_grid(ctx, m);
@@ -972,7 +827,7 @@ static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, co
     if ((rc = true_residual(ctx, m, d_row_ptr, d_col, d_val, d_rhs, d_x, w, bb0, &rel, &est))) return rc;
     while (rounds < o.refine_rounds && est > o.est_tol) {
         DKMC_LAUNCH(ctx, fill_kernel, vg, kVecThreads, 0, m, 0.0, w.e);
-        if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, w.res, w.e, w, o.refine_tol, o.max_iter, o.check_every, &iters, &conv, nullptr, m + 32))) return rc;
+        if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, w.res, w.e, w, o.refine_tol, o.max_iter, o.check_every, &iters, &conv, nullptr))) return rc;
         total += iters;
         DKMC_LAUNCH(ctx, axpy_kernel, vg, kVecThreads, 0, m, 1.0, w.e, d_x);
         ++rounds;
@@ -1010,8 +865,19 @@ constexpr long long kP2pTimeoutCycles = 4000000000ll;  // ~2 s: a lost peer beco
 struct P2pPeers {
     unsigned char *base[DKMC_MAX_RANKS];
     int world, rank;
-    size_t red_off, flag_off;
+    size_t red_off, red2_off, flag_off;   // reduction slots of the per-op kernels / of the persistent PCG, flags
 };
+
+// window = [ vector (m doubles) | slots [2][world][kP2pRedCap] | the same again | flags [8][DKMC_MAX_RANKS] ]
+static size_t window_layout(int m, int world, P2pPeers *P) {
+    const size_t pbytes = (((size_t)m + 64) * sizeof(double) + 255) & ~(size_t)255;
+    const size_t rbytes = (size_t)2 * world * kP2pRedCap * sizeof(double);
+    const size_t fbytes = (size_t)8 * DKMC_MAX_RANKS * sizeof(unsigned long long);
+    P->red_off = pbytes;
+    P->red2_off = pbytes + rbytes;
+    P->flag_off = pbytes + 2 * rbytes;
+    return pbytes + 2 * rbytes + fbytes;
+}
 
 struct DistState {
     ncclComm_t comm = nullptr;
@@ -1023,6 +889,15 @@ struct DistState {
     bool p2p = false;
     unsigned long long seq = 0;    // reductions (slots and flags 0/1 by parity)
     unsigned long long hseq = 0;   // halo exchanges (flags 2/3 by parity)
+    unsigned long long pseq_r = 0, pseq_h = 0;   // the persistent PCG's own sequences (second slot bank, flags 4-7)
+    P2pPeers peers;
+};
+
+// one GPU: the persistent PCG runs the same protocol against a "window" in ordinary device memory
+struct SelfWindow {
+    unsigned char *base = nullptr;
+    int m_cap = 0;
+    unsigned long long pseq_r = 0, pseq_h = 0;
     P2pPeers peers;
 };
 static DistState *dist_of(dkmc_ctx *ctx) { return static_cast<DistState *>(ctx->dist); }
@@ -1058,6 +933,152 @@ struct P2pHalo {
     int send_peer[DKMC_MAX_HALO_SEGMENTS], send_begin[DKMC_MAX_HALO_SEGMENTS], send_end[DKMC_MAX_HALO_SEGMENTS];
     int recv_peer[DKMC_MAX_HALO_SEGMENTS];
 };
+
+#include "pcg_persistent.cuh"
+
+static bool use_persistent_pcg(const dkmc_ctx *ctx) { return !ctx->legacy_cg; }
+
+// CTAs per SM of the persistent PCG.  All CTAs must be resident together (they meet at grid barriers), so the
+// grid is sized to what fits: beside the overlapped pairwise kernel that is what its bounded residency leaves.
+// Returns the CTAs per SM and picks the instantiation (*tight: the 40-register one).
+static int pcg_ctas_per_sm(dkmc_ctx *ctx, bool *tight) {
+    static int occ[2] = {0, 0}, regs[2] = {0, 0};
+    if (!occ[0]) {
+        cudaFuncAttributes fa;
+        regs[0] = cudaFuncGetAttributes(&fa, pcg_persistent_kernel<5>) == cudaSuccess ? fa.numRegs : 48;
+        regs[1] = cudaFuncGetAttributes(&fa, pcg_persistent_kernel<6>) == cudaSuccess ? fa.numRegs : 40;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], pcg_persistent_kernel<5>, kSpmvThreads, 0) != cudaSuccess || occ[0] < 1) occ[0] = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], pcg_persistent_kernel<6>, kSpmvThreads, 0) != cudaSuccess || occ[1] < 1) occ[1] = 1;
+    }
+    static int cfg[4] = {0, -1, 0, -1};   // DKMC_PCG_CPS="alone_cps,alone_tight,overlap_cps,overlap_tight" overrides
+    static bool cfg_read = false;
+    if (!cfg_read) { const char *e = getenv("DKMC_PCG_CPS"); if (e) sscanf(e, "%d,%d,%d,%d", &cfg[0], &cfg[1], &cfg[2], &cfg[3]); cfg_read = true; }
+    const bool overlapped = ctx->pw_pending.active;
+    int t = overlapped ? 1 : 0;
+    if (cfg[overlapped ? 3 : 1] >= 0) t = cfg[overlapped ? 3 : 1] ? 1 : 0;
+    int cps = occ[t];
+    if (overlapped) {
+        // registers and threads the pairwise CTAs hold on every SM (allocation granularity: 8 registers per thread)
+        const int pw_threads = ctx->pw_side_blocks_per_sm * ctx->pw_side_threads;
+        const int pw_regs = pw_threads * ((ctx->pw_regs_per_thread + 7) & ~7);
+        const int mine = kSpmvThreads * ((regs[t] + 7) & ~7);
+        int fit = (65536 - pw_regs) / (mine > 0 ? mine : 1);
+        const int fit_threads = (2048 - pw_threads) / kSpmvThreads;
+        if (fit > fit_threads) fit = fit_threads;
+        if (fit < cps) cps = fit;
+    }
+    const int want = cfg[overlapped ? 2 : 0];
+    if (want > 0 && want < cps) cps = want;
+    *tight = t != 0;
+    return cps < 1 ? 1 : cps;
+}
+
+struct PcgGeometry {
+    int ra, rb, t0, t1, n_cl;
+    P2pPeers peers;
+    P2pHalo halo;
+    unsigned long long *pseq_r, *pseq_h;
+};
+
+static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const int *d_col, const double *d_val,
+                              const double *d_b, double *d_x, const CgWork &w, const PcgGeometry &geo, double tol,
+                              int max_iter, int *iters_out, int *converged, double *bb_out) {
+    PcgArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc;
+    const int n = geo.n_cl;
+    DKMC_REQUIRE((size_t)4 + 2 * (size_t)n <= (size_t)kP2pRedCap, "too many clustered rows for a reduction slot");
+    double *s_vec, *rec, *payload;
+    PcgSync *sync;
+    if ((rc = ensure<double>(ctx, S_CG_S, (size_t)m, &s_vec))) return rc;
+    if ((rc = ensure<double>(ctx, S_CL_REC, (size_t)4 * n + 8, &rec))) return rc;
+    if ((rc = ensure<double>(ctx, S_DIST_RED, (size_t)4 + 2 * (size_t)n + 8, &payload))) return rc;
+    const bool fresh = ctx->slot_ptr[S_PCG_SYNC] == nullptr;
+    if ((rc = ensure<PcgSync>(ctx, S_PCG_SYNC, 1, &sync))) return rc;
+    if (fresh) DKMC_CUDA(cudaMemsetAsync(sync, 0, sizeof(PcgSync), ctx->stream));
+    static const bool want_prof = getenv("DKMC_PCG_PROF") != nullptr;
+    long long *prof = nullptr;
+    if (want_prof) {
+        const bool pfresh = ctx->slot_ptr[S_PCG_PROF] == nullptr;
+        if ((rc = ensure<long long>(ctx, S_PCG_PROF, 8, &prof))) return rc;
+        if (pfresh) DKMC_CUDA(cudaMemsetAsync(prof, 0, 8 * sizeof(long long), ctx->stream));
+    }
+    a.m = m; a.ra = geo.ra; a.rb = geo.rb; a.t0 = geo.t0; a.t1 = geo.t1; a.n_cl = n; a.max_iter = max_iter;
+    a.row_ptr = d_row_ptr; a.col = d_col; a.val = d_val; a.dinv = w.dinv; a.b = d_b; a.tile_info = w.tile_row;
+    a.x = d_x; a.r = w.r[0]; a.w = w.Ap; a.p = w.p; a.s = s_vec;
+    a.P = w.P;
+    a.cs = rec; a.cr = rec + 2 * (size_t)n;
+    a.payload = payload; a.partials = w.partials; a.sync = sync; a.sc = w.sc; a.tol = tol;
+    a.rseq0 = *geo.pseq_r; a.hseq0 = *geo.pseq_h;
+    a.peers = geo.peers; a.halo = geo.halo; a.prof = prof;
+    const int rows = geo.rb - geo.ra, nt = geo.t1 - geo.t0;
+    bool tight = false;
+    int grid = ctx->num_sms * pcg_ctas_per_sm(ctx, &tight);
+    int need = ceil_div(rows > 0 ? rows : 1, kSpmvThreads);
+    if (nt > need) need = nt;
+    if (grid > need) grid = need;
+    if ((size_t)3 * grid > (size_t)ctx->num_sms * 32) grid = ctx->num_sms * 32 / 3;   // partials capacity (cg_workspace)
+    DKMC_CUDA(cudaMemsetAsync(&w.sc->pad, 0, sizeof(int), ctx->stream));
+    if (tight) DKMC_LAUNCH(ctx, pcg_persistent_kernel<6>, grid, kSpmvThreads, 0, a);
+    else DKMC_LAUNCH(ctx, pcg_persistent_kernel<5>, grid, kSpmvThreads, 0, a);
+    CgScalars h;
+    DKMC_CUDA(cudaMemcpyAsync(&h, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h.pad != 0) {
+        set_error("persistent PCG: a wait timed out (code %d: 2 local barrier, 3 neighbour halo, 4 reduction) — a CTA could "
+                  "not become resident or a peer GPU did not answer", h.pad);
+        return DKMC_ERR_CUDA;
+    }
+    *geo.pseq_r = h.rseq_end;
+    *geo.pseq_h = h.hseq_end;
+    *iters_out = h.iters;
+    *converged = (h.rz <= h.stop) ? 1 : 0;
+    if (bb_out) *bb_out = h.bb;
+    return DKMC_OK;
+}
+
+static int self_window(dkmc_ctx *ctx, int m, SelfWindow **out) {
+    SelfWindow *sw = static_cast<SelfWindow *>(ctx->selfwin);
+    if (!sw) { sw = new SelfWindow(); ctx->selfwin = sw; }
+    if (sw->m_cap < m) {
+        if (sw->base) { DKMC_CUDA(cudaStreamSynchronize(ctx->stream)); DKMC_CUDA(cudaFree(sw->base)); sw->base = nullptr; }
+        memset(&sw->peers, 0, sizeof(sw->peers));
+        const size_t bytes = window_layout(m + m / 8, 1, &sw->peers);
+        DKMC_CUDA(cudaMalloc(&sw->base, bytes));
+        DKMC_CUDA(cudaMemsetAsync(sw->base, 0, bytes, ctx->stream));
+        sw->m_cap = m + m / 8;
+        sw->peers.world = 1; sw->peers.rank = 0; sw->peers.base[0] = sw->base;
+        // a new window starts with zeroed flags: restart the sequences — but the local barrier's generation
+        // counter (PcgSync) is monotonic, so keep counting the halo sequence and only rewind the reductions' flags
+        sw->pseq_r = 0;
+    }
+    *out = sw;
+    return DKMC_OK;
+}
+
+void free_solver_state(dkmc_ctx *ctx) {
+    SelfWindow *sw = static_cast<SelfWindow *>(ctx->selfwin);
+    if (sw) {
+        if (sw->base) cudaFree(sw->base);
+        delete sw;
+        ctx->selfwin = nullptr;
+    }
+}
+
+static int run_pcg_persistent_single(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
+                                     const double *d_val, const double *d_b, double *d_x, const CgWork &w, double tol,
+                                     int max_iter, int *iters_out, int *converged, double *bb_out) {
+    (void)nnz;
+    SelfWindow *sw;
+    int rc;
+    if ((rc = self_window(ctx, m, &sw))) return rc;
+    PcgGeometry geo;
+    memset(&geo, 0, sizeof(geo));
+    geo.ra = 0; geo.rb = m; geo.t0 = 0; geo.t1 = w.num_tiles; geo.n_cl = w.n_cl;
+    geo.peers = sw->peers;
+    geo.pseq_r = &sw->pseq_r; geo.pseq_h = &sw->pseq_h;
+    return run_pcg_persistent(ctx, m, d_row_ptr, d_col, d_val, d_b, d_x, w, geo, tol, max_iter, iters_out, converged, bb_out);
+}
 
 // dst[0..k) = sum (or max) over ranks of src[0..k)   (src may alias dst)
 __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers P, unsigned long long seq, int k,
@@ -1290,141 +1311,6 @@ __global__ void __launch_bounds__(kVecThreads) dist_inf_norms_kernel(int ra, int
     }
 }
 
-// ---------------------------------------------------------------- fused compute + exchange kernels (peer memory)
-// With open peer windows an iteration of the distributed PCG is four kernels and no collective call:
-//   SpMV (+ local p.Ap)  ->  update (prologue: all-reduce of p.Ap over peer memory)
-//   ->  reduce_scalars (cluster partial sums, all-reduce of [r.D^-1 r, cluster sums], beta, convergence)
-//   ->  direction (epilogue of the last CTA: push the halo rows of p to the neighbours, wait for theirs)
-__device__ __forceinline__ double *p2p_slot(const P2pPeers &P, int at_rank, int buf, int of_rank) {
-    return reinterpret_cast<double *>(P.base[at_rank] + P.red_off) + ((size_t)buf * P.world + of_rank) * kP2pRedCap;
-}
-
-__global__ void __launch_bounds__(kVecThreads) dist_update_p2p_kernel(P2pPeers P, unsigned long long rseq, int ra, int rb,
-                                                                     double *x, double *r, const double *__restrict__ p,
-                                                                     const double *__restrict__ Ap,
-                                                                     const double *__restrict__ dinv,
-                                                                     const double *pAp_local, double *partials,
-                                                                     CgScalars *sc, double *out) {
-    __shared__ double red[32];
-    __shared__ double s_pAp;
-    if (sc->done) return;
-    const int buf = (int)(rseq & 1ull);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {   // this rank's p.Ap goes to everybody
-        const double v = *pAp_local;
-        for (int q = 0; q < P.world; ++q) p2p_slot(P, q, buf, P.rank)[0] = v;
-        for (int q = 0; q < P.world; ++q) st_release_sys(p2p_flag(P, q, buf, P.rank), rseq);
-    }
-    p2p_wait_all(P, buf, rseq, &sc->pad);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double acc = 0.0;
-        for (int q = 0; q < P.world; ++q) acc += *(const volatile double *)p2p_slot(P, P.rank, buf, q);
-        s_pAp = acc;
-    }
-    __syncthreads();
-    const double alpha = sc->rz / s_pAp;
-    double local = 0.0;
-    for (int i = ra + blockIdx.x * blockDim.x + threadIdx.x; i < rb; i += gridDim.x * blockDim.x) {
-        x[i] += alpha * p[i];
-        double ri = r[i] - alpha * Ap[i];
-        r[i] = ri;
-        local += ri * ri * dinv[i];
-    }
-    double tot = block_sum(local, red);
-    grid_sum_finish(tot, partials, &sc->cnt_b, out, red);
-}
-
-// one CTA: cluster partial sums of r over own rows, all-reduce of red[1 .. 4+n), then beta / convergence
-__global__ void __launch_bounds__(256) dist_reduce_scalars_kernel(P2pPeers P, unsigned long long rseq, int n_cl, int ra,
-                                                                   int rb, const int *__restrict__ seg_start,
-                                                                   const int *__restrict__ seg_len,
-                                                                   const int *__restrict__ mem_row, const double *r,
-                                                                   const double *__restrict__ w, double *red,
-                                                                   CgScalars *sc) {
-    __shared__ double sh[32];
-    if (sc->done) return;
-    const int buf = (int)(rseq & 1ull);
-    const int k = 3 + n_cl;
-    for (int s = threadIdx.x; s < n_cl; s += blockDim.x) {
-        double sum = 0.0;
-        if (seg_start[s] == s) {
-            const int len = seg_len[s];
-            for (int q = 0; q < len; ++q) {
-                const int row = mem_row[s + q];
-                if (row >= ra && row < rb) sum += r[row];
-            }
-        }
-        red[4 + s] = sum;
-    }
-    __syncthreads();
-    for (int q = 0; q < P.world; ++q) {
-        double *slot = p2p_slot(P, q, buf, P.rank);
-        for (int j = threadIdx.x; j < k; j += blockDim.x) slot[j] = red[1 + j];
-    }
-    __syncthreads();
-    for (int q = threadIdx.x; q < P.world; q += blockDim.x) st_release_sys(p2p_flag(P, q, buf, P.rank), rseq);
-    p2p_wait_all(P, buf, rseq, &sc->pad);
-    __syncthreads();
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        double acc = 0.0;
-        for (int q = 0; q < P.world; ++q) acc += ((const volatile double *)p2p_slot(P, P.rank, buf, q))[j];
-        red[1 + j] = acc;
-    }
-    __syncthreads();
-    double c1 = coarse_dot(n_cl, seg_start, w, red + 4, red + 4, sh);
-    if (threadIdx.x == 0) {
-        double rzn = red[1] + c1;
-        sc->beta = rzn / sc->rz;
-        sc->rz = rzn;
-        sc->iters += 1;
-        if (rzn <= sc->stop || sc->iters >= sc->max_iter || !(rzn == rzn)) sc->done = 1;
-    }
-}
-
-// p = D^-1 r + W E^-1 s + beta p over own rows; the last CTA to finish pushes this rank's boundary
-// rows into the neighbours' p vectors and waits for theirs, so the next SpMV finds its halo in place
-__global__ void __launch_bounds__(kVecThreads) dist_direction_p2p_kernel(int ra, int rb, const double *__restrict__ r,
-                                                                        Precond Pc, const double *__restrict__ csum,
-                                                                        double *__restrict__ p, CgScalars *sc, int first,
-                                                                        P2pPeers P, P2pHalo H, unsigned long long hseq) {
-    __shared__ bool is_last;
-    if (!first && sc->done) return;
-    const double beta = first ? 0.0 : sc->beta;
-    bool pushed = false;
-    for (int i = ra + blockIdx.x * blockDim.x + threadIdx.x; i < rb; i += gridDim.x * blockDim.x) {
-        double z = r[i] * Pc.dinv[i];
-        const int s = Pc.pos ? Pc.pos[i] : -1;
-        if (s >= 0) { const int st = Pc.seg_start[s]; z += Pc.w[st] * csum[st]; }
-        const double pv = first ? z : z + beta * p[i];
-        p[i] = pv;
-        // boundary rows go straight into the neighbours' p vectors (every CTA pushes what it computes)
-        for (int sgm = 0; sgm < H.n_send; ++sgm)
-            if (i >= H.send_begin[sgm] && i < H.send_end[sgm]) {
-                reinterpret_cast<double *>(P.base[H.send_peer[sgm]])[i] = pv;
-                pushed = true;
-            }
-    }
-    if (__syncthreads_or(pushed)) __threadfence_system();   // peer stores of this CTA before its arrival below
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&sc->cnt_d, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    const int buf = 2 + (int)(hseq & 1ull);
-    __syncthreads();
-    for (int sgm = threadIdx.x; sgm < H.n_send; sgm += blockDim.x) st_release_sys(p2p_flag(P, H.send_peer[sgm], buf, P.rank), hseq);
-    for (int sgm = threadIdx.x; sgm < H.n_recv; sgm += blockDim.x) {
-        const unsigned long long *f = p2p_flag(P, P.rank, buf, H.recv_peer[sgm]);
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) < hseq) {
-            if (clock64() - t0 > kP2pTimeoutCycles) { sc->pad = 1; break; }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) sc->cnt_d = 0u;
-}
-
 struct DistWork {
     CgWork w;
     const dkmc_dist_plan *plan;
@@ -1483,8 +1369,7 @@ static void fill_halo_desc(const dkmc_dist_plan *pl, P2pHalo *H) {
 // Makes v's own rows and halo available to this rank's SpMV.  Peer memory: the rows are copied into
 // the window (which the search direction does not occupy at that moment) and the boundary rows
 // pushed to the neighbours; *use = the window.  Otherwise NCCL send/recv in place; *use = v.
-static int dist_halo_any(dkmc_ctx *ctx, const DistWork &d, double *v, CgScalars *sc, const double **use, int *readable,
-                         int v_readable) {
+static int dist_halo_any(dkmc_ctx *ctx, const DistWork &d, double *v, CgScalars *sc, const double **use) {
     DistState *ds = dist_of(ctx);
     const int m_rows = d.plan->row_end[ds->world - 1];
     if (ds->p2p && m_rows <= ds->m_cap && !(g_flags & 128)) {
@@ -1495,12 +1380,10 @@ static int dist_halo_any(dkmc_ctx *ctx, const DistWork &d, double *v, CgScalars 
         if (grid > ctx->num_sms * 4) grid = ctx->num_sms * 4;
         DKMC_LAUNCH(ctx, p2p_scatter_rows_kernel, grid, 256, 0, d.ra, d.rb, v, ds->peers, H, ++ds->hseq, &sc->cnt_d, &sc->pad);
         *use = reinterpret_cast<const double *>(ds->win);
-        *readable = ds->m_cap + 32;
         return DKMC_OK;
     }
     int rc = halo_exchange(ctx, d, v);
     *use = v;
-    *readable = v_readable;
     return rc;
 }
 
@@ -1512,17 +1395,29 @@ static int dist_grid(const dkmc_ctx *ctx, int n) {
 
 static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                     const double *d_b, double *d_x, const DistWork &d, double tol, int max_iter, int check_every,
-                    int *iters_out, int *converged, int x_readable) {
+                    int *iters_out, int *converged) {
     DistState *ds = dist_of(ctx);
     const CgWork &w = d.w;
     const int nt = d.t1 - d.t0, rows = d.rb - d.ra, vg = dist_grid(ctx, rows), n = d.n_cl;
+    // open peer windows: the whole solve is ONE persistent kernel per rank (pcg_persistent.cuh) — halo rows
+    // pushed over NVLink from the vector phase, one merged reduction per iteration through peer memory
+    if (use_persistent_pcg(ctx) && ds->p2p && m <= ds->m_cap && (size_t)4 + 2 * (size_t)n <= (size_t)kP2pRedCap) {
+        PcgGeometry geo;
+        memset(&geo, 0, sizeof(geo));
+        geo.ra = d.ra; geo.rb = d.rb; geo.t0 = d.t0; geo.t1 = d.t1; geo.n_cl = n;
+        geo.peers = ds->peers;
+        fill_halo_desc(d.plan, &geo.halo);
+        geo.pseq_r = &ds->pseq_r; geo.pseq_h = &ds->pseq_h;
+        return run_pcg_persistent(ctx, m, d_row_ptr, d_col, d_val, d_b, d_x, w, geo, tol, max_iter, iters_out, converged, nullptr);
+    }
+    // fallback (no peer access, or DKMC_LEGACY_CG=1): one kernel per operation, NCCL (or the per-op peer-memory
+    // all-reduce) between them — three exchanges per iteration
     double *r = w.r[0];
     int rc;
     const double *x_use = d_x;
-    int x_use_readable = x_readable;
-    if ((rc = dist_halo_any(ctx, d, d_x, w.sc, &x_use, &x_use_readable, x_readable))) return rc;
+    if ((rc = dist_halo_any(ctx, d, d_x, w.sc, &x_use))) return rc;
     if ((rc = launch_spmv<2>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, x_use, r, w.tile_row + d.t0, d_b, w.dinv, w.partials,
-                             &w.sc->cnt_c, &w.sc->resnorm2, nullptr, x_use_readable))) return rc;
+                             &w.sc->cnt_c, &w.sc->resnorm2, nullptr))) return rc;
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.dinv, w.partials, &w.sc->cnt_a, d.red + 1);
     DKMC_LAUNCH(ctx, dist_sqnorm_kernel, vg, kVecThreads, 0, d.ra, d.rb, d_b, w.dinv, w.partials, &w.sc->cnt_a, d.red + 2);
     if (n > 0) {
@@ -1531,68 +1426,17 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
     }
     if ((rc = dist_allreduce(ctx, d.red + 1, (size_t)3 + 2 * (size_t)n, w.sc))) return rc;
     DKMC_LAUNCH(ctx, dist_scalars_init_kernel, 1, 256, 0, n, d.seg_start, w.P.w, d.red, tol, max_iter, w.sc);
-    // fused compute + exchange kernels when the windows are open, p lives in this rank's window and the
-    // cluster sums fit a reduction slot
-    const bool fused = ds->p2p && w.p == reinterpret_cast<double *>(ds->win) && (size_t)3 + 2 * (size_t)n <= (size_t)kP2pRedCap &&
-                       !(g_flags & 128);
-    P2pHalo H;
-    memset(&H, 0, sizeof(H));
-    if (fused) {
-        const dkmc_dist_plan *pl = d.plan;
-        H.n_send = pl->n_send; H.n_recv = pl->n_recv;
-        for (int k = 0; k < pl->n_send; ++k) { H.send_peer[k] = pl->send_peer[k]; H.send_begin[k] = pl->send_begin[k]; H.send_end[k] = pl->send_end[k]; }
-        for (int k = 0; k < pl->n_recv; ++k) H.recv_peer[k] = pl->recv_peer[k];
-        DKMC_LAUNCH(ctx, dist_direction_p2p_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.P, d.red + 4, w.p, w.sc, 1, ds->peers, H,
-                    ++ds->hseq);
-    } else {
-        DKMC_LAUNCH(ctx, dist_direction_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.P, d.red + 4, w.p, w.sc, 1);
-    }
+    DKMC_LAUNCH(ctx, dist_direction_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.P, d.red + 4, w.p, w.sc, 1);
     CgScalars h;
     memset(&h, 0, sizeof(h));
     int launched = 0;
     if (check_every < 1) check_every = 1;
     while (true) {
-        static const bool prof = getenv("DKMC_DIST_PROF") != nullptr;
-        static int prof_batches = 0;
-        cudaEvent_t pe[33][5];
-        const bool do_prof = prof && fused && prof_batches < 200 && check_every <= 32 && ds->rank == 0;
-        if (do_prof) for (int a = 0; a < 33; ++a) for (int b = 0; b < 5; ++b) cudaEventCreate(&pe[a][b]);
-        for (int k = 0; k < check_every && fused; ++k) {
-            if (do_prof) cudaEventRecord(pe[k][0], ctx->stream);
-            if (nt > 0) {
-                if ((rc = launch_spmv<1>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap, w.tile_row + d.t0, w.p, nullptr,
-                                         w.partials, &w.sc->cnt_c, d.red + 0, &w.sc->done, m + 32))) return rc;
-            } else
-                DKMC_CUDA(cudaMemsetAsync(d.red, 0, sizeof(double), ctx->stream));
-            if (do_prof) cudaEventRecord(pe[k][1], ctx->stream);
-            DKMC_LAUNCH(ctx, dist_update_p2p_kernel, vg, kVecThreads, 0, ds->peers, ++ds->seq, d.ra, d.rb, d_x, r, w.p, w.Ap,
-                        w.dinv, d.red + 0, w.partials, w.sc, d.red + 1);
-            if (do_prof) cudaEventRecord(pe[k][2], ctx->stream);
-            DKMC_LAUNCH(ctx, dist_reduce_scalars_kernel, 1, 256, 0, ds->peers, ++ds->seq, n, d.ra, d.rb, d.seg_start, d.seg_len,
-                        d.mem_row, r, w.P.w, d.red, w.sc);
-            if (do_prof) cudaEventRecord(pe[k][3], ctx->stream);
-            DKMC_LAUNCH(ctx, dist_direction_p2p_kernel, vg, kVecThreads, 0, d.ra, d.rb, r, w.P, d.red + 4, w.p, w.sc, 0, ds->peers,
-                        H, ++ds->hseq);
-            if (do_prof) cudaEventRecord(pe[k][4], ctx->stream);
-        }
-        if (do_prof) {
-            cudaStreamSynchronize(ctx->stream);
-            double acc[4] = {0, 0, 0, 0};
-            for (int k = 0; k < check_every; ++k)
-                for (int b = 0; b < 4; ++b) { float ms = 0; cudaEventElapsedTime(&ms, pe[k][b], pe[k][b + 1]); acc[b] += ms; }
-            float span = 0;
-            cudaEventElapsedTime(&span, pe[0][0], pe[check_every - 1][4]);
-            fprintf(stderr, "batch %d: us/iter: spmv %.1f update %.1f reduce %.1f direction %.1f | span %.1f\n", prof_batches,
-                    1e3 * acc[0] / check_every, 1e3 * acc[1] / check_every, 1e3 * acc[2] / check_every, 1e3 * acc[3] / check_every,
-                    1e3 * span / check_every);
-            for (int a = 0; a < 33; ++a) for (int b = 0; b < 5; ++b) cudaEventDestroy(pe[a][b]);
-            ++prof_batches;
-        }
-        for (int k = 0; k < check_every && !fused; ++k) {
+        for (int k = 0; k < check_every; ++k) {
             if ((rc = dist_halo_p(ctx, d, w.p, w.sc))) return rc;
             if (nt > 0) {
                 if ((rc = launch_spmv<1>(ctx, nt, m, nnz, d_row_ptr, d_col, d_val, w.p, w.Ap, w.tile_row + d.t0, w.p, nullptr,
-                                         w.partials, &w.sc->cnt_c, d.red + 0, &w.sc->done, m + 32))) return rc;
+                                         w.partials, &w.sc->cnt_c, d.red + 0, &w.sc->done))) return rc;
             } else
                 DKMC_CUDA(cudaMemsetAsync(d.red, 0, sizeof(double), ctx->stream));
             if ((rc = dist_allreduce(ctx, d.red, 1, w.sc))) return rc;
@@ -1627,8 +1471,7 @@ static int dist_true_residual(dkmc_ctx *ctx, int m, int nnz, const int *d_row_pt
     (void)nnz;
     int rc;
     const double *x_use = d_x;
-    int x_use_readable = 0;
-    if ((rc = dist_halo_any(ctx, d, d_x, w.sc, &x_use, &x_use_readable, 0))) return rc;
+    if ((rc = dist_halo_any(ctx, d, d_x, w.sc, &x_use))) return rc;
     if (nt > 0)
         DKMC_LAUNCH(ctx, residual_dd_kernel, nt, kSpmvThreads, 0, m, d_row_ptr, d_col, d_val, x_use, d_rhs, w.dinv, w.res,
                     w.tile_row + d.t0, w.partials, &w.sc->cnt_d, &w.sc->resnorm2);
@@ -1654,17 +1497,17 @@ __global__ void axpy_range_kernel(int ra, int rb, double a, const double *__rest
 
 static int dist_solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                               const double *d_rhs, double *d_x, DistWork &d, const dkmc_solver_opts &o,
-                              dkmc_solve_info *info, int x_readable) {
+                              dkmc_solve_info *info) {
     int iters = 0, conv = 0, total = 0, rc, rounds = 0;
     double est = 0.0;
     const int rows = d.rb - d.ra, vg = dist_grid(ctx, rows);
-    if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, d, o.rel_tol, o.max_iter, o.check_every, &iters, &conv, x_readable))) return rc;
+    if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, d, o.rel_tol, o.max_iter, o.check_every, &iters, &conv))) return rc;
     total += iters;
     bool all_conv = conv != 0;
     if ((rc = dist_true_residual(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, d, &est))) return rc;
     while (rounds < o.refine_rounds && est > o.est_tol) {
         DKMC_CUDA(cudaMemsetAsync(d.w.e, 0, (size_t)m * sizeof(double), ctx->stream));
-        if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d.w.res, d.w.e, d, o.refine_tol, o.max_iter, o.check_every, &iters, &conv, m + 32))) return rc;
+        if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d.w.res, d.w.e, d, o.refine_tol, o.max_iter, o.check_every, &iters, &conv))) return rc;
         total += iters;
         if (rows > 0) DKMC_LAUNCH(ctx, axpy_range_kernel, vg, kVecThreads, 0, d.ra, d.rb, 1.0, d.w.e, d_x);
         ++rounds;
@@ -1691,35 +1534,6 @@ int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_
                           nullptr, nullptr, nullptr);
 }
 
-int dkmc_ctx_set_packed_spmv(dkmc_ctx *ctx, int on) {
-    DKMC_REQUIRE(ctx != nullptr, "ctx");
-    ctx->use_packed_spmv = on ? 1 : 0;
-    if (!on) ctx->packed.val_tag = nullptr;
-    return DKMC_OK;
-}
-
-int dkmc_ctx_set_window_spmv(dkmc_ctx *ctx, int on) {
-    DKMC_REQUIRE(ctx != nullptr, "ctx");
-    ctx->use_window_spmv = on ? 1 : 0;
-    return DKMC_OK;
-}
-
-int dkmc_spmv_window(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
-                     const double *d_x, int x_readable, double *d_y) {
-    DKMC_REQUIRE(ctx && d_row_ptr && d_col && d_val && d_x && d_y, "null pointer");
-    const WinFormat &wf = ctx->win;
-    DKMC_REQUIRE(ctx->use_window_spmv, "the window-staged SpMV is switched off: dkmc_ctx_set_window_spmv(ctx, 1)");
-    DKMC_REQUIRE(wf.ok && wf.row_ptr == d_row_ptr && wf.val_tag == d_val,
-                 "the window-staged format holds another matrix (or this pattern exceeds its limits): call dkmc_assemble_K first");
-    DKMC_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 63) == 0 && x_readable >= ((m + 7) & ~7),
-                 "x must be 64-byte aligned and readable up to the next multiple of 8 entries");
-    const int4 *tile_row;
-    int num_tiles, rc;
-    if ((rc = get_tiling(ctx, m, nnz, d_row_ptr, &tile_row, &num_tiles))) return rc;
-    return launch_spmv<0>(ctx, num_tiles, m, nnz, d_row_ptr, d_col, d_val, d_x, d_y, tile_row, nullptr, nullptr, nullptr,
-                          nullptr, nullptr, nullptr, x_readable);
-}
-
 static int assemble_impl(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int NR, double VL, double VR, int rule,
                          double high_G, double low_G, const int *d_site_element, const int *d_site_charge,
                          const int *d_metals, int num_metals, double *d_val, double *d_rhs);
@@ -1741,30 +1555,11 @@ static int assemble_impl(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, 
     int rc;
     if ((rc = ensure<unsigned char>(ctx, S_CLASS, N, &cls))) return rc;
     if ((rc = ensure<double>(ctx, S_CG_DINV, sp->m, &dinv))) return rc;
-    // the window-staged SpMV format of this pattern (built on first use): the assembly refreshes its
-    // per-step part (high_G bits, diagonal) alongside the CSR values
-    const int4 *tile_row;
-    int num_tiles;
-    if ((rc = get_tiling(ctx, sp->m, sp->nnz, sp->d_row_ptr, &tile_row, &num_tiles))) return rc;
-    if ((rc = get_win_format(ctx, sp->m, sp->nnz, sp->d_row_ptr, sp->d_col, tile_row, num_tiles))) return rc;
-    WinFormat &wf = ctx->win;
-    const bool win_ok = wf.ok && ctx->use_window_spmv && wf.row_ptr == sp->d_row_ptr;
-    if (wf.val_tag == d_val) wf.val_tag = nullptr;
-    PackedCsr &pk = ctx->packed;
-    pk.val_tag = nullptr;
-    pk.pcol = nullptr;
-    if (ctx->use_packed_spmv && sp->m < kPackDiag) {
-        if ((rc = ensure<int>(ctx, S_CG_PCOL, (size_t)sp->nnz, &pk.pcol))) return rc;
-        if ((rc = ensure<double>(ctx, S_CG_PDIAG, (size_t)sp->m, &pk.diag))) return rc;
-    }
     DKMC_LAUNCH(ctx, site_class_kernel, ceil_div(N, 256), 256, 0, N, d_site_element, d_site_charge, d_metals,
                 num_metals, cls);
     DKMC_LAUNCH(ctx, assemble_kernel, ceil_div(sp->m, 128), 128, 0, sp->m, N, NL, NR, VL, VR, rule, high_G, low_G, cls,
                 sp->d_row_ptr, sp->d_col, sp->d_left_row_ptr, sp->d_left_col, sp->d_right_row_ptr, sp->d_right_col,
-                d_val, d_rhs, dinv, wf.code_base, wf.code_pos, wf.diag_pos, win_ok ? wf.blobs : nullptr, pk.pcol,
-                pk.pcol ? pk.diag : nullptr);
-    if (win_ok) { wf.val_tag = d_val; wf.m_high = -high_G; wf.m_low = -low_G; }
-    if (pk.pcol) { pk.val_tag = d_val; pk.row_ptr = sp->d_row_ptr; pk.m_high = -high_G; pk.m_low = -low_G; }
+                d_val, d_rhs, dinv);
     return DKMC_OK;
 }
 
@@ -1779,7 +1574,7 @@ int dkmc_solve_cg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int
     if ((rc = cg_workspace(ctx, m, nnz, d_row_ptr, &w))) return rc;
     DKMC_LAUNCH(ctx, diag_inverse_kernel, ceil_div(m, 256), 256, 0, m, d_row_ptr, d_col, d_val, w.dinv);
     DKMC_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
-    rc = solve_refined(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o, info, m);
+    rc = solve_refined(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, w, o, info);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
     DKMC_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
     DKMC_CUDA(cudaEventSynchronize(ctx->ev_b));
@@ -1839,7 +1634,7 @@ int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int
     }
     // warm start: the interior of the previous potential (potential_solver_gpu.cu:754)
     double *x = d_site_potential_boundary + NL;
-    rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info, m + NR);
+    rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
     // Dirichlet contacts (potential_solver.cpp:389-403 / potential_solver_gpu.cu:768-771)
     if (NL > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NL, 256), 256, 0, NL, -Vd / 2, d_site_potential_boundary);
@@ -1882,7 +1677,7 @@ int dkmc_update_CB_edge_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, in
                             rhs))) return rc;
     DKMC_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
     double *x = d_site_CB_edge + NL;
-    rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info, m + NR);
+    rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
     if (NL > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NL, 256), 256, 0, NL, VL, d_site_CB_edge);
     if (NR > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NR, 256), 256, 0, NR, VR, d_site_CB_edge + (N - NR));
@@ -1900,6 +1695,25 @@ int dkmc_update_CB_edge_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, in
 }
 
 int dkmc_spmv_tile_nnz(void) { return kSpmvTile; }
+
+int dkmc_ctx_set_legacy_cg(dkmc_ctx *ctx, int on) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    ctx->legacy_cg = on ? 1 : 0;
+    return DKMC_OK;
+}
+
+int dkmc_pcg_profile(dkmc_ctx *ctx, double *out7) {
+    DKMC_REQUIRE(ctx && out7, "null pointer");
+    for (int q = 0; q < 7; ++q) out7[q] = 0.0;
+    long long *prof = static_cast<long long *>(ctx->slot_ptr[S_PCG_PROF]);
+    if (!prof) return DKMC_OK;
+    long long h[8];
+    DKMC_CUDA(cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    DKMC_CUDA(cudaMemsetAsync(prof, 0, sizeof(h), ctx->stream));
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < 7; ++q) out7[q] = (double)h[q];
+    return DKMC_OK;
+}
 
 int dkmc_dist_unique_id(char *id128) {
     DKMC_REQUIRE(id128 != nullptr, "id buffer");
@@ -1929,12 +1743,7 @@ int dkmc_dist_p2p_alloc(dkmc_ctx *ctx, int m, char *ipc_handle64) {
     DKMC_REQUIRE(ds != nullptr, "dkmc_dist_init must be called first");
     DKMC_REQUIRE(ds->win == nullptr, "window already allocated");
     static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "cudaIpcMemHandle_t larger than 64 bytes");
-    const size_t pbytes = (((size_t)m + 64) * sizeof(double) + 255) & ~(size_t)255;
-    const size_t rbytes = (size_t)2 * ds->world * kP2pRedCap * sizeof(double);
-    const size_t fbytes = (size_t)4 * DKMC_MAX_RANKS * sizeof(unsigned long long);
-    ds->peers.red_off = pbytes;
-    ds->peers.flag_off = pbytes + rbytes;
-    ds->win_bytes = pbytes + rbytes + fbytes;
+    ds->win_bytes = window_layout(m, ds->world, &ds->peers);
     DKMC_CUDA(cudaMalloc(&ds->win, ds->win_bytes));
     DKMC_CUDA(cudaMemset(ds->win, 0, ds->win_bytes));
     ds->m_cap = m;
@@ -2048,10 +1857,7 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
     if (o.cluster_precond) {
         const unsigned char *cls = static_cast<const unsigned char *>(ctx->slot_ptr[S_CLASS]);
         if ((rc = build_clusters(ctx, m, NL, cls, sp->d_row_ptr, sp->d_col, val, &d.w))) return rc;
-        int *ints = static_cast<int *>(ctx->slot_ptr[S_CL_INT]);
-        const int nb = ceil_div(m, kCompactThreads);
-        DKMC_CUDA(cudaMemcpyAsync(&d.n_cl, ints + 7 * (size_t)m + 2 * (size_t)nb, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        d.n_cl = d.w.n_cl;
         d.seg_start = d.w.P.seg_start; d.seg_len = d.w.P.seg_len; d.mem_row = d.w.P.mem_row;
     }
     DKMC_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
@@ -2070,11 +1876,11 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
         if (d.rb <= d.ra) d.t1 = d.t0;
     }
     if ((rc = ensure<double>(ctx, S_DIST_RED, (size_t)4 + 2 * (size_t)d.n_cl + 8, &d.red))) return rc;
-    // with open peer windows the search direction lives in this rank's window (offset 0), where the
-    // neighbours push their boundary rows
-    if (ds->p2p && m <= ds->m_cap) d.w.p = reinterpret_cast<double *>(ds->win);
+    // fallback path with open peer windows: the search direction lives in this rank's window (offset 0), where
+    // the neighbours' p2p_halo_kernel pushes their boundary rows (the persistent PCG keeps u there instead)
+    if (ds->p2p && m <= ds->m_cap && !use_persistent_pcg(ctx)) d.w.p = reinterpret_cast<double *>(ds->win);
     double *x = d_site_potential_boundary + NL;
-    rc = dist_solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, d, o, info, m + NR);
+    rc = dist_solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, d, o, info);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
     // all-gather of the solution.  Peer memory: own rows into the window, a barrier, every rank pulls
     // the other ranks' rows from their windows, a barrier (the windows are written again in the next solve)

@@ -102,14 +102,17 @@ int dkmc_update_charge(dkmc_ctx *ctx, const int *d_site_element, int *d_site_cha
 
 /* ---- a4 + a5: background potential.  background_potential_gpu_sparse, gpu_solvers.h:139-141
  * (potential_solver_gpu.cu:696-781; CPU semantics potential_solver.cpp:289-410).
- * Assembles K on the neighbour graph, solves the interior system with Jacobi-preconditioned
- * CG warm-started from d_site_potential_boundary, refines with a double-double residual and
- * writes the Dirichlet contacts (-Vd/2, +Vd/2). */
+ * Assembles K on the neighbour graph, solves the interior system with preconditioned CG (Jacobi + one
+ * coarse unknown per uncharged-vacancy cluster) warm-started from d_site_potential_boundary, refines with
+ * a double-double residual and writes the Dirichlet contacts (-Vd/2, +Vd/2).  Each CG run is ONE persistent
+ * kernel (grid barriers between the vector and the SpMV phase, one reduction per iteration, scalars in
+ * registers; csrc/pcg_persistent.cuh) — semantically the loop of iterative_solvers_gpu.cu:424-455. */
 typedef struct {
     double rel_tol;      /* CG stop: ||r||_D^-1 <= rel_tol * ||b||_D^-1   (default 1e-12) */
     int max_iter;        /* per CG run (default 20000) */
     int refine_rounds;   /* max restarts on the double-double residual (default 4) */
-    int check_every;     /* iterations between host convergence polls (default 32) */
+    int check_every;     /* fallback path only (DKMC_LEGACY_CG=1 / no peer access): iterations between host
+                            convergence polls (default 32); the persistent-kernel PCG decides on the device */
     int cluster_precond; /* 1 (default): add one coarse unknown per uncharged-vacancy cluster to the
                             Jacobi preconditioner; 0: plain Jacobi as the reference */
     double refine_tol;   /* relative tolerance of each restart's correction solve (default 1e-6) */
@@ -148,23 +151,6 @@ int dkmc_assemble_K(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, int NL, int N
 /* y = A x, CSR FP64/int32 (replaces cusparseSpMV, iterative_solvers_gpu.cu:411,428) */
 int dkmc_spmv(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
               const double *d_val, const double *d_x, double *d_y);
-/* K has only two distinct off-diagonal values (-high_G, -low_G): dkmc_assemble_K also writes a PACKED
- * form of the matrix it assembled last (int32 column with the choice in bit 31, the diagonal in a
- * per-row array): 4 bytes per non-zero instead of 12.  dkmc_spmv / the CG use it whenever d_val is
- * that matrix; the products and their order are the same, so y is bit-identical.  Default OFF:
- * measured at 1 M sites it is no faster (70.6 us against 65.7 us) — the SpMV is bound by the
- * 26 M gathers of x through L1/L2, not by the 12 bytes per non-zero it streams from DRAM. */
-int dkmc_ctx_set_packed_spmv(dkmc_ctx *ctx, int on);
-/* An experimental third form of the same product: K has two distinct
- * off-diagonal values and a static pattern, so dkmc_assemble_K also keeps a window-staged form of
- * the matrix it assembled last (2 bytes per non-zero, x pieces bulk-copied to shared memory).  d_val
- * must be that matrix; d_x 64-byte aligned with x_readable >= m rounded up to 8 readable entries.
- * Bit-identical to dkmc_spmv.  DKMC_ERR_ARG if the pattern exceeds the format's limits.
- * EXPERIMENTAL and off by default: it moves 4x fewer DRAM bytes but is bound by shared-memory
- * gathers and instruction issue, and is not faster than the CSR kernels inside the CG yet. */
-int dkmc_ctx_set_window_spmv(dkmc_ctx *ctx, int on); /* default off (experimental) */
-int dkmc_spmv_window(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
-                     const double *d_val, const double *d_x, int x_readable, double *d_y);
 int dkmc_solve_cg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
                   const double *d_val, const double *d_rhs, double *d_x,
                   const dkmc_solver_opts *opts, dkmc_solve_info *info);
@@ -308,6 +294,16 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
                                    const int *d_site_charge, const int *d_metals, int num_metals,
                                    double *d_site_potential_boundary, const dkmc_dist_plan *plan,
                                    const dkmc_solver_opts *opts, dkmc_solve_info *info);
+
+/* on = 1: run the CG as one kernel per operation with host convergence polls (the round-1 path, kept as the
+ * A/B baseline and as the fallback without peer access); default 0 (env DKMC_LEGACY_CG=1 sets it at create). */
+int dkmc_ctx_set_legacy_cg(dkmc_ctx *ctx, int on);
+
+/* Measurement aid: with DKMC_PCG_PROF=1 in the environment the persistent PCG accumulates, in CTA 0, the
+ * nanoseconds spent per phase: out[0] set-up of a solve, [1] vector phase, [2] barrier + halo wait, [3] SpMV
+ * phase, [4] barrier + reduction wait; out[5] = iterations, out[6] = solves since the last call (which resets
+ * the counters).  All zero when profiling is off. */
+int dkmc_pcg_profile(dkmc_ctx *ctx, double *out7);
 
 /* Measurement aid (no reference counterpart): achievable FP64 FMA throughput of this GPU in
  * TFLOP/s (8 independent DFMA chains per thread on every SM) — the roofline denominator of the

@@ -10,6 +10,7 @@ rnd_seed_kmc = 1, CPU build, 1 process):
                    Vd = 1.5 V + the rate table (non-zero entries) — every stage of one step
   s_traj_ramp.npz  the kmc_main.cpp:136-279 loop on the shipped V_switch ramp, first 12 KMC steps:
                    per step Vd, executed (i, j) pairs, step time, sha256 of site_element/charge
+  s_traj_ramp100.npz  the same, the full config-1 window: 100 KMC steps (77 bias points)
   s_traj_6V.npz    the same loop at constant Vd = 6 V, 6 KMC steps (many events per step)
   s_substoich.npz  Device::makeSubstoichiometric (Device.cpp:202-233) for other seeds / concentrations than the
                    shipped (4, 0.05): sha256 of site_element after the reference's draw
@@ -201,6 +202,9 @@ if __name__ == "__main__":
         cb_edge()
     if "ramp" in which:
         trajectory("s_traj_ramp.npz", list(zip(p.V_switch, p.t_switch)), 12)
+    if "ramp100" in which:
+        # BASELINE.json config 1 in full: the first 100 KMC steps of the shipped ramp (~15 min of the reference CPU build)
+        trajectory("s_traj_ramp100.npz", list(zip(p.V_switch, p.t_switch)), 100)
     if "6V" in which:
         trajectory("s_traj_6V.npz", [(6.0, 1.0)], 6)
     if "10V" in which:

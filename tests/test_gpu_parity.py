@@ -533,52 +533,44 @@ def cell_sim():
     return p, dev, sim, buf, nc
 
 
-def test_spmv_window_bit_identical_to_csr(cell_sim, torch):
+def test_spmv_reads_the_values_it_is_given(cell_sim, torch):
+    """dkmc_spmv / dkmc_solve_cg take ANY CSR values: no matrix format is cached behind the caller's back
+    (round 1 kept packed / window-staged copies keyed by the pointer; changing val in place went unnoticed)"""
     from devicekmc_b200._capi import check
     p, dev, sim, buf, nc = cell_sim
     lib = dev.ctx.lib
-    check(lib.dkmc_ctx_set_window_spmv(dev.ctx.h, 1))
-    check(lib.dkmc_ctx_set_packed_spmv(dev.ctx.h, 1))
     sp = buf.sparsity(nc, nc)
     val = torch.zeros(sp.nnz, dtype=torch.float64, device="cuda")
     rhs = torch.zeros(sp.m, dtype=torch.float64, device="cuda")
     check(lib.dkmc_assemble_K(dev.ctx.h, C.byref(sp), dev.N, nc, nc, 10.0, p.high_G, p.low_G, buf.site_element.data_ptr(),
                               buf.site_charge.data_ptr(), buf.metal_types.data_ptr(), len(p.metals), val.data_ptr(),
                               rhs.data_ptr()))
-    assert int((val == -p.high_G).sum()) > 0 and int((val == -p.low_G).sum()) > 0
-    pad = (sp.m + 7) // 8 * 8
     g = torch.Generator(device="cuda"); g.manual_seed(3)
-    for trial in range(3):
-        xfull = torch.full((pad,), float("nan"), dtype=torch.float64, device="cuda")  # padding must never be used
-        xfull[:sp.m] = torch.randn(sp.m, dtype=torch.float64, device="cuda", generator=g)
-        y_csr = torch.empty(sp.m, dtype=torch.float64, device="cuda")
-        y_pk = torch.full((sp.m,), 5.0, dtype=torch.float64, device="cuda")
-        y_win = torch.full((sp.m,), 7.0, dtype=torch.float64, device="cuda")
-        # packed CSR (4 bytes per non-zero, what the CG streams) vs plain CSR (a copy of the values is not
-        # "the matrix assembled last", so it goes through the val/col kernel)
-        check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xfull.data_ptr(), y_pk.data_ptr()))
-        vcopy = val.clone()
-        check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, vcopy.data_ptr(), xfull.data_ptr(), y_csr.data_ptr()))
-        torch.cuda.synchronize()
-        assert torch.equal(y_csr, y_pk)
-        check(lib.dkmc_spmv_window(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xfull.data_ptr(), pad,
-                                   y_win.data_ptr()))
-        torch.cuda.synchronize()
-        assert torch.equal(y_csr, y_win)
-    # the format holds the matrix assembled LAST: another values array is refused, never silently used
-    other = val.clone()
-    st = lib.dkmc_spmv_window(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, other.data_ptr(), xfull.data_ptr(), pad,
-                              y_win.data_ptr())
-    assert st == 2  # DKMC_ERR_ARG
-    # the CG through the window-staged kernel reproduces the CSR-kernel solution bit for bit
-    buf.site_potential_boundary.zero_()
-    dev.updatePotential(buf, p, 10.0, n_contact=nc, overlap=False)
-    b_win = buf.site_potential_boundary.clone()
-    check(lib.dkmc_ctx_set_window_spmv(dev.ctx.h, 0))
-    check(lib.dkmc_ctx_set_packed_spmv(dev.ctx.h, 0))
-    buf.site_potential_boundary.zero_()
-    dev.updatePotential(buf, p, 10.0, n_contact=nc, overlap=False)
-    assert float((b_win - buf.site_potential_boundary).abs().max()) <= 1e-13 * float(b_win.abs().max())
+    x = torch.randn(sp.m, dtype=torch.float64, device="cuda", generator=g)
+    y1, y2 = torch.empty_like(x), torch.empty_like(x)
+    check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), x.data_ptr(), y1.data_ptr()))
+    val.mul_(2.0)                                   # same address, other matrix
+    check(lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), x.data_ptr(), y2.data_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(y2, 2.0 * y1)
+
+
+def test_persistent_pcg_matches_per_op_pcg(cell_sim, torch):
+    """the persistent-kernel PCG (Chronopoulos-Gear recurrence, cluster sums by recurrence) and the round-1
+    one-kernel-per-operation PCG solve the same system to the same refined accuracy"""
+    from devicekmc_b200._capi import check
+    p, dev, sim, buf, nc = cell_sim
+    lib = dev.ctx.lib
+    out = {}
+    for legacy in (1, 0):
+        check(lib.dkmc_ctx_set_legacy_cg(dev.ctx.h, legacy))
+        buf.site_potential_boundary.zero_()
+        o = dev.updatePotential(buf, p, 10.0, n_contact=nc, overlap=False)
+        assert o["cg_converged"] and o["cg_est_error"] <= 1e-13
+        out[legacy] = (buf.site_potential_boundary.clone(), o["cg_iterations"])
+    a, b = out[1][0], out[0][0]
+    assert float((a - b).abs().max()) <= 1e-12 * float(a.abs().max())
+    assert out[0][1] <= 1.3 * out[1][1] + 20      # the rearranged recurrence costs no extra iterations to speak of
 
 
 def test_potential_overlap_matches_serial(cell_sim, O, torch):
