@@ -18,7 +18,7 @@ INCLUDE = os.path.join(_ROOT, "include")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-extended-lambda",
-          "-I", INCLUDE, "-I", CSRC]
+          "-I", INCLUDE, "-I", CSRC] + os.environ.get("DKMC_EXTRA_NVCC", "").split()   # experiments only
 
 # per-file extra flags: events.cu keeps the reference's x86-64 rounding (no FMA contraction)
 SOURCES = {

@@ -165,8 +165,11 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
             cfg__ = true;                                                                     \
         }                                                                                     \
     } while (0)
+// the same for a kernel chosen at run time (function pointer): set on every launch, it is a cheap driver call
+#define DKMC_SET_CARVEOUT_FN(fn) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, ::dkmc::window_carveout())
 #else
 #define DKMC_SET_CARVEOUT(kernel) do { } while (0)
+#define DKMC_SET_CARVEOUT_FN(fn) do { } while (0)
 #endif
 
 #define DKMC_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                             \

@@ -65,6 +65,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// polling loads: relaxed (no fence per poll); the waiter fences once after the flag has arrived
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ long long pcg_now() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -104,19 +115,24 @@ __device__ __forceinline__ void pcg_barrier_halo(const PcgArgs &a, unsigned long
         const int buf = kPcgFlagH + (int)(hseq & 1ull);
         if (t == gridDim.x - 1) {
             a.sync->arrive_h = 0u;
-            __threadfence_system();
-            for (int sgm = 0; sgm < a.halo.n_send; ++sgm) st_release_sys(p2p_flag(P, a.halo.send_peer[sgm], buf, P.rank), hseq);
+            if (a.halo.n_send > 0) {
+                __threadfence_system();
+                for (int sgm = 0; sgm < a.halo.n_send; ++sgm) st_release_sys(p2p_flag(P, a.halo.send_peer[sgm], buf, P.rank), hseq);
+            } else {
+                __threadfence();
+            }
             st_release_gpu(&a.sync->gen_h, hseq);
         }
         const long long t0 = clock64();
-        while (ld_acquire_gpu(&a.sync->gen_h) < hseq)
+        while (ld_relaxed_gpu(&a.sync->gen_h) < hseq)
             if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 2; break; }
         for (int sgm = 0; sgm < a.halo.n_recv; ++sgm) {
             const unsigned long long *f = p2p_flag(P, P.rank, buf, a.halo.recv_peer[sgm]);
-            while (ld_acquire_sys(f) < hseq)
+            while (ld_relaxed_sys(f) < hseq)
                 if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 3; break; }
         }
-        __threadfence();   // as cooperative-groups' grid sync: what other SMs / GPUs wrote is now visible to plain loads
+        // as cooperative-groups' grid sync: after this fence what other SMs / GPUs wrote is visible to plain loads
+        if (a.halo.n_recv > 0) __threadfence_system(); else __threadfence();
     }
     __syncthreads();
 }
@@ -137,32 +153,52 @@ __device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned lo
         s_last = (atomicAdd(&a.sync->arrive_r, 1u) == gridDim.x - 1);
     }
     __syncthreads();
+    const bool multi = P.world > 1;
     if (s_last) {
         __threadfence();
         const int G = (int)gridDim.x;
-        for (int q = 0; q < 4; ++q) {
-            double acc = 0.0;
-            if (q < nparts)
-                for (int i = threadIdx.x; i < G; i += blockDim.x) acc += __ldcg(a.partials + (size_t)q * G + i);
-            acc = block_sum(acc, sh);
-            if (threadIdx.x == 0) s_loc[q] = acc;
+        // the CTA partials in index order; the loads of all arrays in flight together
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int i = threadIdx.x; i < G; i += blockDim.x) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < nparts) acc[q] += __ldcg(a.partials + (size_t)q * G + i);
         }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (q < nparts) acc[q] = block_sum(acc[q], sh);
+            if (threadIdx.x == 0) s_loc[q] = q < nparts ? acc[q] : 0.0;
+        }
+        if (threadIdx.x == 0) s_loc[3] = 0.0;
         __syncthreads();
         for (int q = 0; q < P.world; ++q) {
             double *slot = pcg_slot(P, q, buf, P.rank);
             for (int j = threadIdx.x; j < K; j += blockDim.x) slot[j] = j < 4 ? s_loc[j] : __ldcg(a.payload + j);
         }
         __syncthreads();
-        if (threadIdx.x == 0) { a.sync->arrive_r = 0u; __threadfence_system(); }
+        if (threadIdx.x == 0) {
+            a.sync->arrive_r = 0u;
+            if (multi) __threadfence_system(); else __threadfence();
+        }
         __syncthreads();
-        for (int q = threadIdx.x; q < P.world; q += blockDim.x) st_release_sys(p2p_flag(P, q, kPcgFlagR + buf, P.rank), rseq);
+        if (multi) {
+            for (int q = threadIdx.x; q < P.world; q += blockDim.x) st_release_sys(p2p_flag(P, q, kPcgFlagR + buf, P.rank), rseq);
+        } else if (threadIdx.x == 0) {
+            st_release_gpu(p2p_flag(P, 0, kPcgFlagR + buf, 0), rseq);
+        }
     }
     for (int q = threadIdx.x; q < P.world; q += blockDim.x) {
         const unsigned long long *f = p2p_flag(P, P.rank, kPcgFlagR + buf, q);
         const long long t0 = clock64();
-        while (ld_acquire_sys(f) < rseq)
-            if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 4; break; }
-        __threadfence();
+        if (multi) {
+            while (ld_relaxed_sys(f) < rseq)
+                if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 4; break; }
+            __threadfence_system();
+        } else {
+            while (ld_relaxed_gpu(f) < rseq)
+                if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 4; break; }
+            __threadfence();
+        }
     }
     __syncthreads();
     if (threadIdx.x < 4) out[threadIdx.x] = pcg_reduced(P, buf, threadIdx.x);
@@ -179,9 +215,19 @@ __device__ __forceinline__ double pcg_warp_row_dot(const PcgArgs &a, const doubl
     return warp_sum(s);
 }
 
+// experiment switch (never the default): gathers through the non-coherent path
+#ifdef DKMC_PCG_GATHER_NC
+#define PCG_GATHER(ptr) __ldg(ptr)
+#else
+#define PCG_GATHER(ptr) (*(ptr))
+#endif
+
 // SpMV over the own tiles: y = A g (MODE 1, returns the CTA's share of y.g) or y = b - A g (MODE 2).
-// Same tile algorithm as spmv_tile_kernel: the tile's val/col streamed coalesced, eight per thread in flight,
-// products parked in shared memory, every row added in CSR order.
+// The tile algorithm of spmv_tile_kernel: the tile's val/col streamed coalesced in two batches of four per
+// thread, products parked in shared memory, every row added in CSR order.  What bounds it is latency times
+// the tiles in flight per SM (measured: a software-pipelined version with all sixteen loads of the next tile
+// in flight needed 64 registers, ran 4 CTAs per SM instead of 6 and was slower), so the phase is written to
+// live in the 40 registers that keep six CTAs resident.
 template <int MODE>
 __device__ __forceinline__ double pcg_spmv_tiles(const PcgArgs &a, const double *g, double *y, double *prod) {
     double local = 0.0;
@@ -191,7 +237,8 @@ __device__ __forceinline__ double pcg_spmv_tiles(const PcgArgs &a, const double 
         if (r0 < r1) {
             const int k0 = ti.z, k1 = ti.w;
             const int ka = k0 & ~1;
-            int my_r = r0 + threadIdx.x, ra = 0, rb = 0;
+            const int my_r = r0 + (int)threadIdx.x;
+            int ra = 0, rb = 0;
             if (my_r < r1) { ra = __ldg(a.row_ptr + my_r); rb = __ldg(a.row_ptr + my_r + 1); }
             if (k1 - ka <= kSpmvCap) {
 #pragma unroll
@@ -205,10 +252,23 @@ __device__ __forceinline__ double pcg_spmv_tiles(const PcgArgs &a, const double 
                         v[u] = ok ? __ldcs(a.val + k) : 0.0;
                         c[u] = ok ? __ldcs(a.col + k) : 0;
                     }
+                    // ptxas otherwise issues the first gather right after the first column load and sinks the
+                    // value loads next to their products — the warp then stalls with two loads in flight.  Make
+                    // every gather address depend on ALL eight loads of the batch (columns are non-negative, so
+                    // `zero` is 0 — which the assembler cannot know).
+                    int zero;
+                    {
+                        const int c_or = c[0] | c[1] | c[2] | c[3];
+                        const int v_or = __double2hiint(v[0]) | __double2hiint(v[1]) | __double2hiint(v[2]) | __double2hiint(v[3]);
+                        asm("{ .reg .u32 t; shr.u32 t, %1, 31; and.b32 %0, t, %2; }" : "=r"(zero) : "r"(c_or), "r"(v_or));
+                    }
+                    double xg[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) xg[u] = PCG_GATHER(g + c[u] + zero);   // masked entries read g[0]: harmless
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int k = k0 + (h * 4 + u) * kSpmvThreads + threadIdx.x;
-                        if (k < k1) prod[k - ka] = v[u] * g[c[u]];
+                        if (k < k1) prod[k - ka] = v[u] * xg[u];
                     }
                 }
                 __syncthreads();
@@ -231,7 +291,7 @@ __device__ __forceinline__ double pcg_spmv_tiles(const PcgArgs &a, const double 
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // prod is reused by the next tile
     }
     return local;
 }
@@ -243,7 +303,10 @@ __device__ __forceinline__ void pcg_cluster_rows(const PcgArgs &a, const double 
     const int n = a.n_cl;
     if (n <= 0) return;
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    for (int s = (int)blockIdx.x * wpb + (threadIdx.x >> 5); s < n; s += (int)gridDim.x * wpb) {
+    // dealt out one per CTA from the END of the grid (the first CTAs are the ones that hold one more SpMV tile),
+    // the next round to the next warp: a CTA's warps work in parallel, so the phase grows by one cluster at most
+    const int G = (int)gridDim.x;
+    for (int s = (G - 1 - (int)blockIdx.x) + (int)(threadIdx.x >> 5) * G; s < n; s += G * wpb) {
         double acc = 0.0, accb = 0.0;
         if (__ldg(a.P.seg_start + s) == s) {
             const int len = __ldg(a.P.seg_len + s);
@@ -262,24 +325,33 @@ __device__ __forceinline__ void pcg_cluster_rows(const PcgArgs &a, const double 
     }
 }
 
-// MINB = CTAs per SM the register budget allows: 5 (48 registers) on an SM of its own, 6 (40 registers, a few
-// spilled scalars) when the overlapped pairwise kernel holds part of the register file
-template <int MINB>
+// MINB = CTAs per SM the register budget allows: 6 (40 registers) as the stand-alone SpMV kernel, 5 (48), 4 (64).
+// The scalars of the recurrence live in SHARED memory between the phases (every CTA keeps its own identical
+// copy), not in registers: a phase then needs no more registers than the same code as a kernel of its own.
+struct PcgState {
+    double alpha, beta, gamma, stop, bb;
+    int done, err;
+};
+
+template <int MINB, bool PROF>
 __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(const PcgArgs a) {
     __shared__ __align__(16) double prod[kSpmvCap];
     __shared__ double red[32];
     __shared__ double s_out[4];
+    __shared__ PcgState st;
     const P2pPeers &P = a.peers;
     const int G = (int)gridDim.x, B = (int)blockDim.x, cta = (int)blockIdx.x, tid = (int)threadIdx.x;
     const int n = a.n_cl;
     double *g = reinterpret_cast<double *>(P.base[P.rank]);   // u: own rows + the neighbours' boundary rows
-    unsigned long long rseq = a.rseq0, hseq = a.hseq0;
     const bool clustered = a.P.pos != nullptr && n > 0;
-    long long tp = 0, prof[5] = {0, 0, 0, 0, 0};
-    const bool do_prof = a.prof != nullptr && cta == 0 && tid == 0;
+    long long tp = 0, prof[6] = {0, 0, 0, 0, 0, 0}, cp_s = 0, cp_w = 0, cp_t = 0;
+    const bool do_prof = PROF && cta == 0 && tid == 0;
+    const bool cta_prof = PROF && tid == 0;   // every CTA: its SpMV-phase time and its wait at barrier R
     if (do_prof) tp = pcg_now();
-#define PCG_PROF(slot) do { if (do_prof) { const long long now__ = pcg_now(); prof[slot] += now__ - tp; tp = now__; } } while (0)
+#define PCG_PROF(slot) do { if (PROF && do_prof) { const long long now__ = pcg_now(); prof[slot] += now__ - tp; tp = now__; } } while (0)
 
+    // sequence numbers: set-up uses halo exchanges hseq0+1, +2 and reductions rseq0+1, +2; iteration `it` (from 0)
+    // uses hseq0+3+it and rseq0+3+it
     // ---- init 0: u := x over the own rows (the SpMV gathers from the window), boundary rows to the neighbours
     {
         bool pushed = false;
@@ -288,15 +360,15 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
             g[i] = v;
             pushed |= pcg_push(a.halo, P, i, v);
         }
-        pcg_barrier_halo(a, ++hseq, pushed);
+        pcg_barrier_halo(a, a.hseq0 + 1, pushed);
     }
     // ---- init 1: r = b - A x; cluster sums of r and of b
     pcg_spmv_tiles<2>(a, g, a.r, prod);
     if (clustered) pcg_cluster_rows<2>(a, g);
-    pcg_barrier_reduce(a, ++rseq, 0, 4 + 2 * n, s_out, red);
+    pcg_barrier_reduce(a, a.rseq0 + 1, 0, 4 + 2 * n, s_out, red);
     // ---- init 2: u = M^-1 r (into the window), gamma and b.M^-1 b partials, recurrence state
     {
-        const int rb_ = (int)(rseq & 1ull);
+        const int rb_ = (int)((a.rseq0 + 1) & 1ull);
         double lg = 0.0, lbb = 0.0;
         bool pushed = false;
         for (int i = a.ra + cta * B + tid; i < a.rb; i += G * B) {
@@ -304,10 +376,10 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
             double un = ri * di, zb = bi * di;
             const int sp = clustered ? __ldg(a.P.pos + i) : -1;
             if (sp >= 0) {
-                const int st = __ldg(a.P.seg_start + sp);
-                const double we = __ldg(a.P.w + st);
-                un += we * pcg_reduced(P, rb_, 4 + st);
-                zb += we * pcg_reduced(P, rb_, 4 + n + st);
+                const int s0 = __ldg(a.P.seg_start + sp);
+                const double we = __ldg(a.P.w + s0);
+                un += we * pcg_reduced(P, rb_, 4 + s0);
+                zb += we * pcg_reduced(P, rb_, 4 + n + s0);
             }
             g[i] = un;
             pushed |= pcg_push(a.halo, P, i, un);
@@ -320,7 +392,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
         __syncthreads();
         lbb = block_sum(lbb, red);
         if (tid == 0) { a.partials[cta] = lg; a.partials[2 * (size_t)G + cta] = lbb; }
-        pcg_barrier_halo(a, ++hseq, pushed);
+        pcg_barrier_halo(a, a.hseq0 + 2, pushed);
     }
     // ---- init 3: w = A u; delta partial; cluster sums of w
     {
@@ -328,24 +400,29 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
         if (clustered) pcg_cluster_rows<1>(a, g);
         ld = block_sum(ld, red);
         if (tid == 0) a.partials[(size_t)G + cta] = ld;
-        pcg_barrier_reduce(a, ++rseq, 3, 4 + n, s_out, red);
+        const bool err = pcg_barrier_reduce(a, a.rseq0 + 2, 3, 4 + n, s_out, red);
+        if (tid == 0) {
+            const double gamma = s_out[0], delta = s_out[1], bb = s_out[2];
+            st.gamma = gamma; st.bb = bb;
+            st.stop = a.tol * a.tol * (bb > 0.0 ? bb : gamma);
+            st.alpha = gamma / delta; st.beta = 0.0;
+            st.done = (gamma <= st.stop || !(gamma == gamma)) ? 1 : 0;
+            st.err = err ? 1 : 0;
+        }
+        __syncthreads();
     }
-    double gamma = s_out[0], delta = s_out[1];
-    const double bb = s_out[2];
-    const double stop = a.tol * a.tol * (bb > 0.0 ? bb : gamma);
-    double alpha = gamma / delta, beta = 0.0;
-    int iters = 0, par = 0;
-    bool done = gamma <= stop || !(gamma == gamma);
-    bool err = false;
     PCG_PROF(0);
 
-    while (!done && !err && iters < a.max_iter) {
+    int it = 0;
+    for (; it < a.max_iter && !st.done && !st.err; ++it) {
         // ---- V: p, s, x, r, u over the own rows; gamma partial
         {
-            const int rb_ = (int)(rseq & 1ull);
+            const double alpha = st.alpha, beta = st.beta;
+            const int rb_ = (int)((a.rseq0 + 2 + it) & 1ull);   // parity of the latest reduction
+            const int par = it & 1;
             const double *cs_old = a.cs + (size_t)par * n, *cr_old = a.cr + (size_t)par * n;
             double *cs_new = a.cs + (size_t)(par ^ 1) * n, *cr_new = a.cr + (size_t)(par ^ 1) * n;
-            const bool first = iters == 0;
+            const bool first = it == 0;
             double lg = 0.0;
             bool pushed = false;
             for (int i = a.ra + cta * B + tid; i < a.rb; i += G * B) {
@@ -362,9 +439,9 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
                 a.r[i] = ri;
                 double un = ri * di;
                 if (sp >= 0) {
-                    const int st = __ldg(a.P.seg_start + sp);
-                    const double csn = pcg_reduced(P, rb_, 4 + st) + beta * cs_old[st];
-                    un += __ldg(a.P.w + st) * (cr_old[st] - alpha * csn);
+                    const int s0 = __ldg(a.P.seg_start + sp);
+                    const double csn = pcg_reduced(P, rb_, 4 + s0) + beta * cs_old[s0];
+                    un += __ldg(a.P.w + s0) * (cr_old[s0] - alpha * csn);
                 }
                 g[i] = un;
                 pushed |= pcg_push(a.halo, P, i, un);
@@ -376,43 +453,54 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
                     cs_new[s] = csn;
                     cr_new[s] = cr_old[s] - alpha * csn;
                 }
-            par ^= 1;
             lg = block_sum(lg, red);
             if (tid == 0) a.partials[cta] = lg;
             PCG_PROF(1);
-            pcg_barrier_halo(a, ++hseq, pushed);
+            pcg_barrier_halo(a, a.hseq0 + 3 + it, pushed);
             PCG_PROF(2);
         }
         // ---- S: w = A u; delta partial; cluster sums of w; the one reduction of the iteration
         {
+            if (PROF && cta_prof) cp_t = pcg_now();
             double ld = pcg_spmv_tiles<1>(a, g, a.w, prod);
+            PCG_PROF(3);
             if (clustered) pcg_cluster_rows<1>(a, g);
             ld = block_sum(ld, red);
             if (tid == 0) a.partials[(size_t)G + cta] = ld;
-            PCG_PROF(3);
-            err = pcg_barrier_reduce(a, ++rseq, 2, 4 + n, s_out, red);
             PCG_PROF(4);
+            if (PROF && cta_prof) { const long long now = pcg_now(); cp_s += now - cp_t; cp_t = now; }
+            const bool err = pcg_barrier_reduce(a, a.rseq0 + 3 + it, 2, 4 + n, s_out, red);
+            if (PROF && cta_prof) cp_w += pcg_now() - cp_t;
+            PCG_PROF(5);
+            if (tid == 0) {
+                const double gamma_new = s_out[0], delta = s_out[1];
+                const double beta = gamma_new / st.gamma;
+                st.alpha = gamma_new / (delta - beta * gamma_new / st.alpha);
+                st.beta = beta;
+                st.gamma = gamma_new;
+                st.done = (gamma_new <= st.stop || !(gamma_new == gamma_new)) ? 1 : 0;
+                st.err = err ? 1 : 0;
+            }
+            __syncthreads();
         }
-        const double gamma_new = s_out[0];
-        delta = s_out[1];
-        beta = gamma_new / gamma;
-        alpha = gamma_new / (delta - beta * gamma_new / alpha);
-        gamma = gamma_new;
-        ++iters;
-        done = gamma <= stop || !(gamma == gamma);
+    }
+    if (PROF && cta_prof) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.prof[8 + 2 * cta] += cp_s;
+        a.prof[9 + 2 * cta] = (a.prof[9 + 2 * cta] & ~0xfffll) + (cp_w << 12) + (long long)(smid & 0xfffu);   // wait | SM id
     }
     if (cta == 0 && tid == 0) {
         CgScalars *sc = a.sc;
-        sc->rz = gamma; sc->bb = bb; sc->stop = stop; sc->iters = iters; sc->max_iter = a.max_iter;
-        sc->done = done ? 1 : 0;
-        sc->alpha = alpha; sc->beta = beta;
-        sc->rseq_end = rseq; sc->hseq_end = hseq;
-        if (a.prof) {
-            for (int q = 0; q < 5; ++q) a.prof[q] += prof[q];
-            a.prof[5] += iters;
-            a.prof[6] += 1;
+        sc->rz = st.gamma; sc->bb = st.bb; sc->stop = st.stop; sc->iters = it; sc->max_iter = a.max_iter;
+        sc->done = st.done;
+        sc->alpha = st.alpha; sc->beta = st.beta;
+        sc->rseq_end = a.rseq0 + 2 + it; sc->hseq_end = a.hseq0 + 2 + it;
+        if (PROF) {
+            for (int q = 0; q < 6; ++q) a.prof[q] += prof[q];
+            a.prof[6] += it;
+            a.prof[7] += 1;
         }
     }
 #undef PCG_PROF
 }
-

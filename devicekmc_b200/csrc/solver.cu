@@ -14,7 +14,9 @@
 //     (uncharged-vacancy clusters coupled by high_G inside a low_G oxide) takes from plain CG.
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 #define DKMC_CARVEOUT_MAXSHARED 1
@@ -937,31 +939,39 @@ struct P2pHalo {
 #include "pcg_persistent.cuh"
 
 static bool use_persistent_pcg(const dkmc_ctx *ctx) { return !ctx->legacy_cg; }
+constexpr int kPcgProfLen = 8 + 2 * 2048;   // phase sums of CTA 0 | per CTA: SpMV-phase time, wait at barrier R
 
 // CTAs per SM of the persistent PCG.  All CTAs must be resident together (they meet at grid barriers), so the
 // grid is sized to what fits: beside the overlapped pairwise kernel that is what its bounded residency leaves.
-// Returns the CTAs per SM and picks the instantiation (*tight: the 40-register one).
-static int pcg_ctas_per_sm(dkmc_ctx *ctx, bool *tight) {
-    static int occ[2] = {0, 0}, regs[2] = {0, 0};
+// Three instantiations trade registers per thread (loads in flight) against CTAs per SM: *variant = 0, 1, 2 for
+// launch bounds of 6, 5, 4 CTAs per SM (40, 48, 64 registers).
+typedef void (*PcgKernel)(const PcgArgs);
+static const PcgKernel kPcgKernels[3] = {pcg_persistent_kernel<6, false>, pcg_persistent_kernel<5, false>, pcg_persistent_kernel<4, false>};
+static const PcgKernel kPcgKernelsProf[3] = {pcg_persistent_kernel<6, true>, pcg_persistent_kernel<5, true>, pcg_persistent_kernel<4, true>};
+
+static int pcg_ctas_per_sm(dkmc_ctx *ctx, int *variant) {
+    static int occ[3] = {0, 0, 0}, regs[3] = {0, 0, 0};
     if (!occ[0]) {
-        cudaFuncAttributes fa;
-        regs[0] = cudaFuncGetAttributes(&fa, pcg_persistent_kernel<5>) == cudaSuccess ? fa.numRegs : 48;
-        regs[1] = cudaFuncGetAttributes(&fa, pcg_persistent_kernel<6>) == cudaSuccess ? fa.numRegs : 40;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], pcg_persistent_kernel<5>, kSpmvThreads, 0) != cudaSuccess || occ[0] < 1) occ[0] = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], pcg_persistent_kernel<6>, kSpmvThreads, 0) != cudaSuccess || occ[1] < 1) occ[1] = 1;
+        for (int v = 0; v < 3; ++v) {
+            cudaFuncAttributes fa;
+            regs[v] = cudaFuncGetAttributes(&fa, kPcgKernels[v]) == cudaSuccess ? fa.numRegs : 40 + 8 * v;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], kPcgKernels[v], kSpmvThreads, 0) != cudaSuccess || occ[v] < 1) occ[v] = 1;
+        }
     }
-    static int cfg[4] = {0, -1, 0, -1};   // DKMC_PCG_CPS="alone_cps,alone_tight,overlap_cps,overlap_tight" overrides
+    // DKMC_PCG_CPS="alone_cps,alone_variant,overlap_cps,overlap_variant" overrides (0 / -1: default)
+    static int cfg[4] = {0, -1, 0, -1};
     static bool cfg_read = false;
     if (!cfg_read) { const char *e = getenv("DKMC_PCG_CPS"); if (e) sscanf(e, "%d,%d,%d,%d", &cfg[0], &cfg[1], &cfg[2], &cfg[3]); cfg_read = true; }
     const bool overlapped = ctx->pw_pending.active;
-    int t = overlapped ? 1 : 0;
-    if (cfg[overlapped ? 3 : 1] >= 0) t = cfg[overlapped ? 3 : 1] ? 1 : 0;
-    int cps = occ[t];
+    int v = 0;
+    const int cv = cfg[overlapped ? 3 : 1];
+    if (cv >= 0 && cv < 3) v = cv;
+    int cps = occ[v];
     if (overlapped) {
         // registers and threads the pairwise CTAs hold on every SM (allocation granularity: 8 registers per thread)
         const int pw_threads = ctx->pw_side_blocks_per_sm * ctx->pw_side_threads;
         const int pw_regs = pw_threads * ((ctx->pw_regs_per_thread + 7) & ~7);
-        const int mine = kSpmvThreads * ((regs[t] + 7) & ~7);
+        const int mine = kSpmvThreads * ((regs[v] + 7) & ~7);
         int fit = (65536 - pw_regs) / (mine > 0 ? mine : 1);
         const int fit_threads = (2048 - pw_threads) / kSpmvThreads;
         if (fit > fit_threads) fit = fit_threads;
@@ -969,7 +979,7 @@ static int pcg_ctas_per_sm(dkmc_ctx *ctx, bool *tight) {
     }
     const int want = cfg[overlapped ? 2 : 0];
     if (want > 0 && want < cps) cps = want;
-    *tight = t != 0;
+    *variant = v;
     return cps < 1 ? 1 : cps;
 }
 
@@ -1000,8 +1010,8 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
     long long *prof = nullptr;
     if (want_prof) {
         const bool pfresh = ctx->slot_ptr[S_PCG_PROF] == nullptr;
-        if ((rc = ensure<long long>(ctx, S_PCG_PROF, 8, &prof))) return rc;
-        if (pfresh) DKMC_CUDA(cudaMemsetAsync(prof, 0, 8 * sizeof(long long), ctx->stream));
+        if ((rc = ensure<long long>(ctx, S_PCG_PROF, kPcgProfLen, &prof))) return rc;
+        if (pfresh) DKMC_CUDA(cudaMemsetAsync(prof, 0, kPcgProfLen * sizeof(long long), ctx->stream));
     }
     a.m = m; a.ra = geo.ra; a.rb = geo.rb; a.t0 = geo.t0; a.t1 = geo.t1; a.n_cl = n; a.max_iter = max_iter;
     a.row_ptr = d_row_ptr; a.col = d_col; a.val = d_val; a.dinv = w.dinv; a.b = d_b; a.tile_info = w.tile_row;
@@ -1012,15 +1022,25 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
     a.rseq0 = *geo.pseq_r; a.hseq0 = *geo.pseq_h;
     a.peers = geo.peers; a.halo = geo.halo; a.prof = prof;
     const int rows = geo.rb - geo.ra, nt = geo.t1 - geo.t0;
-    bool tight = false;
-    int grid = ctx->num_sms * pcg_ctas_per_sm(ctx, &tight);
+    int variant = 0;
+    int grid = ctx->num_sms * pcg_ctas_per_sm(ctx, &variant);
     int need = ceil_div(rows > 0 ? rows : 1, kSpmvThreads);
     if (nt > need) need = nt;
     if (grid > need) grid = need;
     if ((size_t)3 * grid > (size_t)ctx->num_sms * 32) grid = ctx->num_sms * 32 / 3;   // partials capacity (cg_workspace)
+    if (grid > 2048) grid = 2048;
     DKMC_CUDA(cudaMemsetAsync(&w.sc->pad, 0, sizeof(int), ctx->stream));
-    if (tight) DKMC_LAUNCH(ctx, pcg_persistent_kernel<6>, grid, kSpmvThreads, 0, a);
-    else DKMC_LAUNCH(ctx, pcg_persistent_kernel<5>, grid, kSpmvThreads, 0, a);
+    {
+        const PcgKernel kern = (prof ? kPcgKernelsProf : kPcgKernels)[variant];
+        DKMC_SET_CARVEOUT_FN(kern);
+        kern<<<grid, kSpmvThreads, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        cudaError_t err__ = cudaPeekAtLastError();
+        if (err__ != cudaSuccess) {
+            set_error("%s:%d: launch of pcg_persistent_kernel failed: %s", __FILE__, __LINE__, cudaGetErrorString(err__));
+            return DKMC_ERR_CUDA;
+        }
+    }
     CgScalars h;
     DKMC_CUDA(cudaMemcpyAsync(&h, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1702,16 +1722,38 @@ int dkmc_ctx_set_legacy_cg(dkmc_ctx *ctx, int on) {
     return DKMC_OK;
 }
 
-int dkmc_pcg_profile(dkmc_ctx *ctx, double *out7) {
-    DKMC_REQUIRE(ctx && out7, "null pointer");
-    for (int q = 0; q < 7; ++q) out7[q] = 0.0;
+int dkmc_pcg_profile(dkmc_ctx *ctx, double *out8) {
+    DKMC_REQUIRE(ctx && out8, "null pointer");
+    for (int q = 0; q < 8; ++q) out8[q] = 0.0;
     long long *prof = static_cast<long long *>(ctx->slot_ptr[S_PCG_PROF]);
     if (!prof) return DKMC_OK;
-    long long h[8];
-    DKMC_CUDA(cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    DKMC_CUDA(cudaMemsetAsync(prof, 0, sizeof(h), ctx->stream));
+    std::vector<long long> h(kPcgProfLen);
+    DKMC_CUDA(cudaMemcpyAsync(h.data(), prof, kPcgProfLen * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    DKMC_CUDA(cudaMemsetAsync(prof, 0, kPcgProfLen * sizeof(long long), ctx->stream));
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int q = 0; q < 7; ++q) out7[q] = (double)h[q];
+    for (int q = 0; q < 8; ++q) out8[q] = (double)h[q];
+    if (getenv("DKMC_PCG_PROF_CTAS") && h[6] > 0) {   // spread over the CTAs (dev aid)
+        std::vector<std::pair<long long, int>> sv;
+        long long wmin = 1ll << 62, wmax = 0;
+        for (int c = 0; c < 2048; ++c) {
+            const long long s_ns = h[8 + 2 * c], w_ns = h[9 + 2 * c] >> 12;
+            if (s_ns == 0 && w_ns == 0) continue;
+            sv.push_back({s_ns, c});
+            if (w_ns < wmin) wmin = w_ns;
+            if (w_ns > wmax) wmax = w_ns;
+        }
+        std::sort(sv.begin(), sv.end());
+        const double it = (double)h[6] * 1e3;
+        const size_t n = sv.size();
+        fprintf(stderr, "dkmc pcg prof: %zu CTAs; SpMV phase us/it min %.1f p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f; wait at barrier R min %.1f max %.1f; slowest (cta@sm):",
+                n, sv[0].first / it, sv[n / 10].first / it, sv[n / 2].first / it, sv[n * 9 / 10].first / it, sv[n * 99 / 100].first / it,
+                sv[n - 1].first / it, wmin / it, wmax / it);
+        for (size_t q = 0; q < 10 && q < n; ++q) {
+            const int c = sv[n - 1 - q].second;
+            fprintf(stderr, " %d@%d(%.1f)", c, (int)(h[9 + 2 * c] & 0xfff), sv[n - 1 - q].first / it);
+        }
+        fprintf(stderr, "\n");
+    }
     return DKMC_OK;
 }
 

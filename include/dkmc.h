@@ -301,9 +301,9 @@ int dkmc_ctx_set_legacy_cg(dkmc_ctx *ctx, int on);
 
 /* Measurement aid: with DKMC_PCG_PROF=1 in the environment the persistent PCG accumulates, in CTA 0, the
  * nanoseconds spent per phase: out[0] set-up of a solve, [1] vector phase, [2] barrier + halo wait, [3] SpMV
- * phase, [4] barrier + reduction wait; out[5] = iterations, out[6] = solves since the last call (which resets
- * the counters).  All zero when profiling is off. */
-int dkmc_pcg_profile(dkmc_ctx *ctx, double *out7);
+ * tiles, [4] cluster rows, [5] barrier + reduction wait; out[6] = iterations, out[7] = solves since the last
+ * call (which resets the counters).  All zero when profiling is off. */
+int dkmc_pcg_profile(dkmc_ctx *ctx, double *out8);
 
 /* Measurement aid (no reference counterpart): achievable FP64 FMA throughput of this GPU in
  * TFLOP/s (8 independent DFMA chains per thread on every SM) — the roofline denominator of the

@@ -24,7 +24,7 @@ for legacy in (1, 0):
     check(lib.dkmc_ctx_set_legacy_cg(dev.ctx.h, legacy))
     for overlap in (False, True):
         ts, outs = [], []
-        prof = (C.c_double * 7)()
+        prof = (C.c_double * 8)()
         check(lib.dkmc_pcg_profile(dev.ctx.h, prof))
         for rep in range(3):
             buf.site_potential_boundary.copy_(w0)
@@ -39,21 +39,26 @@ for legacy in (1, 0):
         line = "%s overlap=%d total %s ms | cg %.2f ms %d its = %.1f us/it | pw %.2f ms | est %.1e conv %s | vs first %.1e" % (
             "per-op    " if legacy else "persistent", overlap, "/".join("%.1f" % t for t in ts), o["solve_ms"], o["cg_iterations"],
             1e3 * o["solve_ms"] / max(o["cg_iterations"], 1), o["pairwise_ms"], o["cg_est_error"], o["cg_converged"], err)
-        if prof[5] > 0:
-            it = prof[5]
-            line += " | prof us/it: V %.1f barH %.1f S %.1f barR %.1f; setup %.0f us/solve (%d solves)" % (
-                prof[1] / it / 1e3, prof[2] / it / 1e3, prof[3] / it / 1e3, prof[4] / it / 1e3, prof[0] / max(prof[6], 1) / 1e3, prof[6])
+        if prof[6] > 0:
+            it = prof[6]
+            line += " | prof us/it: V %.1f barH %.1f S %.1f cl %.1f barR %.1f; setup %.0f us/solve (%d solves)" % (
+                prof[1] / it / 1e3, prof[2] / it / 1e3, prof[3] / it / 1e3, prof[4] / it / 1e3, prof[5] / it / 1e3,
+                prof[0] / max(prof[7], 1) / 1e3, prof[7])
         print(line, flush=True)
 '''
 
 name = sys.argv[1] if len(sys.argv) > 1 else "tiled_1M"
-configs = sys.argv[2:] or ["", "6,0,3,1", "5,0,2,0", "4,0,2,1", "3,0,1,0"]
+configs = sys.argv[2:] or ["6,0,3,0", "6,0,3,0p", "5,1,2,1", "4,2,2,2"]
 for cfg in configs:
-    env = dict(os.environ, DKMC_PCG_PROF="1")
+    env = dict(os.environ)
+    if cfg.endswith("p"):      # "...p": with the in-kernel profile (its kernels carry extra registers: timings are distorted)
+        cfg = cfg[:-1]
+        env.update(DKMC_PCG_PROF="1", DKMC_PCG_PROF_CTAS="1")
     if cfg:
         env["DKMC_PCG_CPS"] = cfg
-    print("=== DKMC_PCG_CPS=%r (alone_cps,alone_tight,overlap_cps,overlap_tight)" % cfg, flush=True)
+    print("=== DKMC_PCG_CPS=%r (alone_cps,alone_variant,overlap_cps,overlap_variant; variant 0/1/2 = 40/48/64 registers)" % cfg, flush=True)
     r = subprocess.run([sys.executable, "-c", CHILD, name], env=env, capture_output=True, text=True)
     print(r.stdout, end="")
+    print("\n".join(l for l in r.stderr.splitlines() if "pcg prof" in l))
     if r.returncode != 0:
         print("FAILED:", r.stderr[-3000:])
