@@ -82,15 +82,41 @@ __device__ __forceinline__ long long pcg_now() {
     return t;
 }
 
-// second bank of reduction slots (the per-op kernels keep the first)
-__device__ __forceinline__ double *pcg_slot(const P2pPeers &P, int at_rank, int buf, int of_rank) {
-    return reinterpret_cast<double *>(P.base[at_rank] + P.red2_off) + ((size_t)buf * P.world + of_rank) * kP2pRedCap;
+// Reductions travel in the second bank of slots as self-validating words (the "LL" idea of NCCL): a double goes
+// as two 8-byte words {low half | seq << 32}, {high half | seq << 32}, each one store, so a reader that finds the
+// sequence number in both words has the value — no flag after the data, hence no system-scope fence at the
+// sender and no acquire at the reader (a release.sys store alone cost ~8 us per reduction).
+__device__ __forceinline__ unsigned long long *pcg_slot(const P2pPeers &P, int at_rank, int buf, int of_rank) {
+    return reinterpret_cast<unsigned long long *>(P.base[at_rank] + P.red2_off) + ((size_t)buf * P.world + of_rank) * kP2pRedCap;
 }
+constexpr int kPcgMaxPayload = kP2pRedCap / 2;   // doubles per reduction (two words each)
 
-// sum over the ranks (in rank order) of entry j of the reduction with parity `buf`, as it arrived here
-__device__ __forceinline__ double pcg_reduced(const P2pPeers &P, int buf, int j) {
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void pcg_ll_store(unsigned long long *slot, int j, double v, unsigned int seq) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v), tag = (unsigned long long)seq << 32;
+    st_relaxed_sys(slot + 2 * j, tag | (bits & 0xffffffffull));
+    st_relaxed_sys(slot + 2 * j + 1, tag | (bits >> 32));
+}
+// entry j of rank q's contribution to reduction `seq`, as it arrived here (spins until it has)
+__device__ __forceinline__ double pcg_ll_load(const P2pPeers &P, int buf, int q, int j, unsigned int seq, int *err) {
+    const unsigned long long *w = pcg_slot(P, P.rank, buf, q) + 2 * j;
+    unsigned long long a = ld_relaxed_sys(w), b = ld_relaxed_sys(w + 1);
+    if ((unsigned int)(a >> 32) != seq || (unsigned int)(b >> 32) != seq) {
+        const long long t0 = clock64();
+        do {
+            a = ld_relaxed_sys(w); b = ld_relaxed_sys(w + 1);
+            if (clock64() - t0 > kP2pTimeoutCycles) { *err = 4; break; }
+        } while ((unsigned int)(a >> 32) != seq || (unsigned int)(b >> 32) != seq);
+    }
+    return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+}
+// sum over the ranks (in rank order) of entry j of reduction `seq`
+__device__ __forceinline__ double pcg_reduced(const P2pPeers &P, unsigned long long rseq, int j, int *err) {
+    const int buf = (int)(rseq & 1ull);
     double acc = 0.0;
-    for (int q = 0; q < P.world; ++q) acc += *(reinterpret_cast<const volatile double *>(pcg_slot(P, P.rank, buf, q)) + j);
+    for (int q = 0; q < P.world; ++q) acc += pcg_ll_load(P, buf, q, j, (unsigned int)rseq, err);
     return acc;
 }
 
@@ -108,19 +134,20 @@ __device__ __forceinline__ bool pcg_push(const P2pHalo &H, const P2pPeers &P, in
 // and so are the neighbours' boundary rows in this rank's window.
 __device__ __forceinline__ void pcg_barrier_halo(const PcgArgs &a, unsigned long long hseq, bool pushed) {
     const P2pPeers &P = a.peers;
-    const bool any = __syncthreads_or(pushed);
+    (void)pushed;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        if (any) __threadfence_system(); else __threadfence();
+        // gpu scope is enough also for the rows this CTA stored into the neighbours' windows: the chain
+        // store -> fence.gpu -> arrival (atomic) -> last CTA's fence -> its st.release.sys flag -> the neighbour's
+        // ld.acquire.sys is a causality chain in the PTX memory model, and system-wide fences in every CTA are
+        // what made these exchanges slow (15-20 us per barrier, measured)
+        __threadfence();
         const unsigned int t = atomicAdd(&a.sync->arrive_h, 1u);
         const int buf = kPcgFlagH + (int)(hseq & 1ull);
         if (t == gridDim.x - 1) {
             a.sync->arrive_h = 0u;
-            if (a.halo.n_send > 0) {
-                __threadfence_system();
-                for (int sgm = 0; sgm < a.halo.n_send; ++sgm) st_release_sys(p2p_flag(P, a.halo.send_peer[sgm], buf, P.rank), hseq);
-            } else {
-                __threadfence();
-            }
+            __threadfence();
+            for (int sgm = 0; sgm < a.halo.n_send; ++sgm) st_release_sys(p2p_flag(P, a.halo.send_peer[sgm], buf, P.rank), hseq);
             st_release_gpu(&a.sync->gen_h, hseq);
         }
         const long long t0 = clock64();
@@ -131,29 +158,33 @@ __device__ __forceinline__ void pcg_barrier_halo(const PcgArgs &a, unsigned long
             while (ld_relaxed_sys(f) < hseq)
                 if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 3; break; }
         }
-        // as cooperative-groups' grid sync: after this fence what other SMs / GPUs wrote is visible to plain loads
-        if (a.halo.n_recv > 0) __threadfence_system(); else __threadfence();
+        // the acquire that ends the wait (and invalidates L1: plain loads now see what other SMs / GPUs wrote)
+        if (a.halo.n_recv > 0) (void)ld_acquire_sys(p2p_flag(P, P.rank, buf, a.halo.recv_peer[0]));
+        else (void)ld_acquire_gpu(&a.sync->gen_h);
     }
     __syncthreads();
 }
 
 // Barrier R + all-reduce.  On entry every CTA has written its `nparts` partial sums (partials[q * grid + cta])
-// and the cluster warps their entries of a.payload[4 ..).  On return out[0 .. 3] hold the global sums of the
-// partial arrays, and the slots of parity (rseq & 1) the cluster entries of every rank.  K = payload length.
+// and the cluster warps their entries of a.payload[4 ..).  The last CTA to arrive adds the partials in index
+// order and sends [sums | cluster entries] to every rank (LL words); every CTA then waits for the four leading
+// words of every rank — this rank's own words double as the local barrier release — and adds them in rank
+// order: out[0 .. 3] = global sums.  The cluster entries are read where they are needed (pcg_reduced).
+// K = payload length.  Returns true if a wait timed out somewhere on this GPU.
 __device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned long long rseq, int nparts, int K,
                                                    double *out, double *sh) {
     const P2pPeers &P = a.peers;
     __shared__ bool s_last;
-    __shared__ int s_err;
     __shared__ double s_loc[4];
+    __shared__ int s_err;
     const int buf = (int)(rseq & 1ull);
+    const unsigned int seq = (unsigned int)rseq;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         s_last = (atomicAdd(&a.sync->arrive_r, 1u) == gridDim.x - 1);
     }
     __syncthreads();
-    const bool multi = P.world > 1;
     if (s_last) {
         __threadfence();
         const int G = (int)gridDim.x;
@@ -169,40 +200,34 @@ __device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned lo
             if (q < nparts) acc[q] = block_sum(acc[q], sh);
             if (threadIdx.x == 0) s_loc[q] = q < nparts ? acc[q] : 0.0;
         }
-        if (threadIdx.x == 0) s_loc[3] = 0.0;
+        if (threadIdx.x == 0) { s_loc[3] = 0.0; a.sync->arrive_r = 0u; }
         __syncthreads();
+        // remote ranks first (their words are self-validating), the cluster entries of this rank, and last —
+        // behind a fence — this rank's four leading words: whoever reads them may read everything written
+        // on this GPU before the barrier
         for (int q = 0; q < P.world; ++q) {
-            double *slot = pcg_slot(P, q, buf, P.rank);
-            for (int j = threadIdx.x; j < K; j += blockDim.x) slot[j] = j < 4 ? s_loc[j] : __ldcg(a.payload + j);
+            if (q == P.rank) continue;
+            unsigned long long *slot = pcg_slot(P, q, buf, P.rank);
+            for (int j = threadIdx.x; j < K; j += blockDim.x) pcg_ll_store(slot, j, j < 4 ? s_loc[j] : __ldcg(a.payload + j), seq);
         }
+        unsigned long long *mine = pcg_slot(P, P.rank, buf, P.rank);
+        for (int j = 4 + threadIdx.x; j < K; j += blockDim.x) pcg_ll_store(mine, j, __ldcg(a.payload + j), seq);
         __syncthreads();
         if (threadIdx.x == 0) {
-            a.sync->arrive_r = 0u;
-            if (multi) __threadfence_system(); else __threadfence();
-        }
-        __syncthreads();
-        if (multi) {
-            for (int q = threadIdx.x; q < P.world; q += blockDim.x) st_release_sys(p2p_flag(P, q, kPcgFlagR + buf, P.rank), rseq);
-        } else if (threadIdx.x == 0) {
-            st_release_gpu(p2p_flag(P, 0, kPcgFlagR + buf, 0), rseq);
+            __threadfence();
+            for (int j = 0; j < 4; ++j) pcg_ll_store(mine, j, s_loc[j], seq);
         }
     }
-    for (int q = threadIdx.x; q < P.world; q += blockDim.x) {
-        const unsigned long long *f = p2p_flag(P, P.rank, kPcgFlagR + buf, q);
-        const long long t0 = clock64();
-        if (multi) {
-            while (ld_relaxed_sys(f) < rseq)
-                if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 4; break; }
-            __threadfence_system();
-        } else {
-            while (ld_relaxed_gpu(f) < rseq)
-                if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 4; break; }
-            __threadfence();
-        }
+    if (threadIdx.x == 0) s_err = 0;
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        int err = 0;
+        out[threadIdx.x] = pcg_reduced(P, rseq, threadIdx.x, &err);
+        __threadfence();   // acquire side of the local barrier (fence - relaxed store / relaxed load - fence)
+        if (err) { s_err = err; a.sc->pad = err; }
     }
     __syncthreads();
-    if (threadIdx.x < 4) out[threadIdx.x] = pcg_reduced(P, buf, threadIdx.x);
-    if (threadIdx.x == 0) s_err = *reinterpret_cast<volatile int *>(&a.sc->pad);   // a wait timed out somewhere on this GPU
+    if (threadIdx.x == 0 && s_err == 0) s_err = *reinterpret_cast<volatile int *>(&a.sc->pad);   // a timeout elsewhere on this GPU
     __syncthreads();
     return s_err != 0;
 }
@@ -344,6 +369,10 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
     const int n = a.n_cl;
     double *g = reinterpret_cast<double *>(P.base[P.rank]);   // u: own rows + the neighbours' boundary rows
     const bool clustered = a.P.pos != nullptr && n > 0;
+    // vector phases: a contiguous chunk of the own rows per CTA, so that only the CTAs at the slab faces store
+    // into the neighbours' windows
+    const int chunk = (a.rb - a.ra + G - 1) / G;
+    const int v0 = a.ra + cta * chunk, v1 = min(a.rb, v0 + chunk);
     long long tp = 0, prof[6] = {0, 0, 0, 0, 0, 0}, cp_s = 0, cp_w = 0, cp_t = 0;
     const bool do_prof = PROF && cta == 0 && tid == 0;
     const bool cta_prof = PROF && tid == 0;   // every CTA: its SpMV-phase time and its wait at barrier R
@@ -355,7 +384,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
     // ---- init 0: u := x over the own rows (the SpMV gathers from the window), boundary rows to the neighbours
     {
         bool pushed = false;
-        for (int i = a.ra + cta * B + tid; i < a.rb; i += G * B) {
+        for (int i = v0 + tid; i < v1; i += B) {
             const double v = a.x[i];
             g[i] = v;
             pushed |= pcg_push(a.halo, P, i, v);
@@ -368,18 +397,19 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
     pcg_barrier_reduce(a, a.rseq0 + 1, 0, 4 + 2 * n, s_out, red);
     // ---- init 2: u = M^-1 r (into the window), gamma and b.M^-1 b partials, recurrence state
     {
-        const int rb_ = (int)((a.rseq0 + 1) & 1ull);
+        const unsigned long long rs_ = a.rseq0 + 1;
+        int lerr = 0;
         double lg = 0.0, lbb = 0.0;
         bool pushed = false;
-        for (int i = a.ra + cta * B + tid; i < a.rb; i += G * B) {
+        for (int i = v0 + tid; i < v1; i += B) {
             const double ri = a.r[i], bi = __ldg(a.b + i), di = __ldg(a.dinv + i);
             double un = ri * di, zb = bi * di;
             const int sp = clustered ? __ldg(a.P.pos + i) : -1;
             if (sp >= 0) {
                 const int s0 = __ldg(a.P.seg_start + sp);
                 const double we = __ldg(a.P.w + s0);
-                un += we * pcg_reduced(P, rb_, 4 + s0);
-                zb += we * pcg_reduced(P, rb_, 4 + n + s0);
+                un += we * pcg_reduced(P, rs_, 4 + s0, &lerr);
+                zb += we * pcg_reduced(P, rs_, 4 + n + s0, &lerr);
             }
             g[i] = un;
             pushed |= pcg_push(a.halo, P, i, un);
@@ -387,7 +417,8 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
             lbb += bi * zb;
         }
         for (int s = cta * B + tid; s < n; s += G * B)
-            if (__ldg(a.P.seg_start + s) == s) { a.cr[s] = pcg_reduced(P, rb_, 4 + s); a.cs[s] = 0.0; }
+            if (__ldg(a.P.seg_start + s) == s) { a.cr[s] = pcg_reduced(P, rs_, 4 + s, &lerr); a.cs[s] = 0.0; }
+        if (lerr) a.sc->pad = lerr;
         lg = block_sum(lg, red);
         __syncthreads();
         lbb = block_sum(lbb, red);
@@ -418,14 +449,15 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
         // ---- V: p, s, x, r, u over the own rows; gamma partial
         {
             const double alpha = st.alpha, beta = st.beta;
-            const int rb_ = (int)((a.rseq0 + 2 + it) & 1ull);   // parity of the latest reduction
+            const unsigned long long rs_ = a.rseq0 + 2 + it;   // the latest reduction
+            int lerr = 0;
             const int par = it & 1;
             const double *cs_old = a.cs + (size_t)par * n, *cr_old = a.cr + (size_t)par * n;
             double *cs_new = a.cs + (size_t)(par ^ 1) * n, *cr_new = a.cr + (size_t)(par ^ 1) * n;
             const bool first = it == 0;
             double lg = 0.0;
             bool pushed = false;
-            for (int i = a.ra + cta * B + tid; i < a.rb; i += G * B) {
+            for (int i = v0 + tid; i < v1; i += B) {
                 // every load before the first store: the vectors may alias as far as the compiler knows, and a
                 // load behind a store would wait for it (three dependent round trips per pass instead of one)
                 const double ui = g[i], wi = a.w[i], xi = a.x[i], ro = a.r[i], di = __ldg(a.dinv + i);
@@ -440,7 +472,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
                 double un = ri * di;
                 if (sp >= 0) {
                     const int s0 = __ldg(a.P.seg_start + sp);
-                    const double csn = pcg_reduced(P, rb_, 4 + s0) + beta * cs_old[s0];
+                    const double csn = pcg_reduced(P, rs_, 4 + s0, &lerr) + beta * cs_old[s0];
                     un += __ldg(a.P.w + s0) * (cr_old[s0] - alpha * csn);
                 }
                 g[i] = un;
@@ -449,10 +481,11 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
             }
             for (int s = cta * B + tid; s < n; s += G * B)
                 if (__ldg(a.P.seg_start + s) == s) {
-                    const double csn = pcg_reduced(P, rb_, 4 + s) + beta * cs_old[s];
+                    const double csn = pcg_reduced(P, rs_, 4 + s, &lerr) + beta * cs_old[s];
                     cs_new[s] = csn;
                     cr_new[s] = cr_old[s] - alpha * csn;
                 }
+            if (lerr) a.sc->pad = lerr;
             lg = block_sum(lg, red);
             if (tid == 0) a.partials[cta] = lg;
             PCG_PROF(1);

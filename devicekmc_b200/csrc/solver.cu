@@ -997,7 +997,7 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
     memset(&a, 0, sizeof(a));
     int rc;
     const int n = geo.n_cl;
-    DKMC_REQUIRE((size_t)4 + 2 * (size_t)n <= (size_t)kP2pRedCap, "too many clustered rows for a reduction slot");
+    DKMC_REQUIRE((size_t)4 + 2 * (size_t)n <= (size_t)kPcgMaxPayload, "too many clustered rows for a reduction slot");
     double *s_vec, *rec, *payload;
     PcgSync *sync;
     if ((rc = ensure<double>(ctx, S_CG_S, (size_t)m, &s_vec))) return rc;
@@ -1421,7 +1421,7 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
     const int nt = d.t1 - d.t0, rows = d.rb - d.ra, vg = dist_grid(ctx, rows), n = d.n_cl;
     // open peer windows: the whole solve is ONE persistent kernel per rank (pcg_persistent.cuh) — halo rows
     // pushed over NVLink from the vector phase, one merged reduction per iteration through peer memory
-    if (use_persistent_pcg(ctx) && ds->p2p && m <= ds->m_cap && (size_t)4 + 2 * (size_t)n <= (size_t)kP2pRedCap) {
+    if (use_persistent_pcg(ctx) && ds->p2p && m <= ds->m_cap && (size_t)4 + 2 * (size_t)n <= (size_t)kPcgMaxPayload) {
         PcgGeometry geo;
         memset(&geo, 0, sizeof(geo));
         geo.ra = d.ra; geo.rb = d.rb; geo.t0 = d.t0; geo.t1 = d.t1; geo.n_cl = n;

@@ -133,6 +133,8 @@ class SlabSim:
         # the pairwise kernel's share of each SM while it runs beside the CG: the fewer targets a rank
         # owns, the smaller the share it needs to finish before the CG does
         share = (3, 128) if world == 1 else ((2, 128) if world == 2 else (1, 128))
+        if os.environ.get("DKMC_PW_SHARE"):     # experiments: "blocks_per_sm,threads"
+            share = tuple(int(v) for v in os.environ["DKMC_PW_SHARE"].split(","))
         from ._capi import check
         check(self.dev.ctx.lib.dkmc_ctx_set_pairwise_share(self.dev.ctx.h, share[0], share[1]))
         self.dcg = None
@@ -145,8 +147,9 @@ class SlabSim:
                 self.dcg.close()
                 self.dcg = None
 
-    def step(self, Vd: float):
+    def step(self, Vd: float, record_events: int = 0):
         import devicekmc_b200 as D
+        from . import _capi
         from ._capi import SolveInfo, check
         dev, buf, p, lib = self.dev, self.buf, self.p, self.dev.ctx.lib
         dev.updateCharge(buf, p.metals)
@@ -159,7 +162,7 @@ class SlabSim:
         if self.i1 > self.i0:
             check(lib.dkmc_poisson_gridless_begin(*pw_args))
         if self.dcg is not None:
-            self.dcg.solve(Vd, info)
+            st = self.dcg.solve(Vd, info)
         else:
             st = lib.dkmc_background_potential_sparse(
                 dev.ctx.h, C.byref(self.sp), dev.N, buf.nn_, buf.neigh_idx.data_ptr(), self.nc, self.nc, float(Vd),
@@ -177,11 +180,33 @@ class SlabSim:
             else:
                 mine = self._pc_full[self.rank * self.chunk:(self.rank + 1) * self.chunk].clone()
                 self.dist.all_gather_into_tensor(self._pc_full, mine)
-        t = self.sim.executeKMCStep(buf, dev)
-        return {"cg_iterations": info.iterations, "solve_ms": info.solve_ms, "assemble_ms": info.assemble_ms,
+        t = self.sim.executeKMCStep(buf, dev, record_events=record_events)
+        return {"cg_iterations": info.iterations, "cg_converged": st == _capi.DKMC_OK, "cg_est_error": info.est_error,
+                "solve_ms": info.solve_ms, "assemble_ms": info.assemble_ms,
                 "pairwise_ms": pw_ms.value,
                 "events": self.sim.last_info.n_events, "fallbacks": self.sim.last_info.n_exact_fallbacks,
                 "loop_ms": self.sim.last_info.loop_ms, "rate_ms": self.sim.last_info.rate_ms, "step_time": t}
+
+
+def multi_vs_single_step(multi: "SlabSim", arrays, p, Vd: float) -> dict:
+    """One step from multi's current state through the distributed path and through a single-GPU SlabSim built
+    on this rank (same state, same KMC random stream); returns the differences."""
+    import torch
+    single = SlabSim(arrays, p, 0, 1, distributed_cg=False)
+    for name in ("site_element", "site_charge", "site_potential_boundary", "site_potential_charge"):
+        getattr(single.buf, name).copy_(getattr(multi.buf, name))
+    single.sim.random_generator._bg.state = multi.sim.random_generator._bg.state
+    a = multi.step(Vd, record_events=1 << 16)
+    ev_m = multi.sim.last_events.copy()
+    b = single.step(Vd, record_events=1 << 16)
+    ev_s = single.sim.last_events.copy()
+    rel = lambda u, v: float((u - v).abs().max() / v.abs().max())
+    return {"phi_b_rel": rel(multi.buf.site_potential_boundary, single.buf.site_potential_boundary),
+            "phi_c_rel": rel(multi.buf.site_potential_charge, single.buf.site_potential_charge),
+            "elements_equal": bool(torch.equal(multi.buf.site_element, single.buf.site_element)),
+            "charges_equal": bool(torch.equal(multi.buf.site_charge, single.buf.site_charge)),
+            "events_equal": bool(a["events"] == b["events"] and np.array_equal(ev_m, ev_s)), "events": int(a["events"]),
+            "cg_converged": bool(a["cg_converged"] and b["cg_converged"])}
 
 
 def bench_multi_gpu(args, metric: str, unit: str):
@@ -213,6 +238,15 @@ def bench_multi_gpu(args, metric: str, unit: str):
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)          # device time, max over ranks
     launches = s.dev.ctx.launch_count() - launches0
+    prof = None
+    if os.environ.get("DKMC_PCG_PROF"):    # in-kernel phase profile of the persistent PCG (rank 0's CTA 0), dev aid
+        buf8 = (C.c_double * 8)()
+        s.dev.ctx.lib.dkmc_pcg_profile(s.dev.ctx.h, buf8)
+        it = max(buf8[6], 1.0)
+        prof = {"us_per_iteration": {"vector": buf8[1] / it / 1e3, "barrier_halo": buf8[2] / it / 1e3, "spmv_tiles": buf8[3] / it / 1e3,
+                                     "cluster_rows": buf8[4] / it / 1e3, "barrier_reduce": buf8[5] / it / 1e3},
+                "setup_us_per_solve": buf8[0] / max(buf8[7], 1.0) / 1e3, "iterations": buf8[6], "solves": buf8[7],
+                "note": "profiling kernels carry extra registers: the timings of such a run are not bench values"}
     # e2e: host buffers in and out every step, on every rank
     ckpt.restore(s.buf, s.sim, s.dev)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -224,12 +258,24 @@ def bench_multi_gpu(args, metric: str, unit: str):
     e1.record(); e1.synchronize()
     ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    # all ranks must hold the same state (replicated event loop on identical inputs)
-    chk = torch.tensor([float(s.buf.site_element.sum().item()), float(s.buf.site_charge.abs().sum().item())],
-                       dtype=torch.float64, device="cuda")
-    lo, hi = chk.clone(), chk.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    consistent = bool(torch.equal(lo, hi))
+    # all ranks must hold the same state, bit for bit (replicated event loop on identical inputs)
+    import hashlib
+    digest = hashlib.sha256(s.buf.site_element.cpu().numpy().tobytes() + s.buf.site_charge.cpu().numpy().tobytes()).hexdigest()
+    digests = [None] * world
+    dist.all_gather_object(digests, digest)
+    consistent = len(set(digests)) == 1
+    # parity, driver-visible: one more step through the distributed path AND through the single-GPU path
+    # (replicated on every rank) from the same state; integers identical, potentials within 1e-10
+    parity = multi_vs_single_step(s, (el, x, y, z), p, args.vd)
+    worst = [None] * world
+    dist.all_gather_object(worst, parity)
+    parity = {"phi_b_rel": max(w["phi_b_rel"] for w in worst), "phi_c_rel": max(w["phi_c_rel"] for w in worst),
+              "elements_equal": all(w["elements_equal"] for w in worst), "charges_equal": all(w["charges_equal"] for w in worst),
+              "events_equal": all(w["events_equal"] for w in worst), "events": worst[0]["events"],
+              "cg_converged": all(w["cg_converged"] for w in worst), "tolerance": 1e-10,
+              "what": "one extra step after the timed region: distributed path vs single-GPU path on every rank, same state and random stream"}
+    parity["ok"] = bool(parity["phi_b_rel"] <= 1e-10 and parity["phi_c_rel"] <= 1e-10 and parity["elements_equal"] and
+                        parity["charges_equal"] and parity["events_equal"] and parity["cg_converged"])
     if rank == 0:
         clocks = sampler.stop()
         value = args.steps / (ms.item() * 1e-3)
@@ -247,8 +293,11 @@ def bench_multi_gpu(args, metric: str, unit: str):
                         "d2h_bytes_per_step": s.buf.d2h_bytes()},
                 "stage_ms": {"cg_solve": med("solve_ms"), "pairwise_concurrent": med("pairwise_ms"),
                              "assemble": med("assemble_ms"), "rate_table": med("rate_ms"),
-                             "event_loop": med("loop_ms")},
+                             "event_loop": med("loop_ms"),
+                             "cg_us_per_iteration": 1e3 * float(np.sum([t["solve_ms"] for t in stats])) /
+                                                    max(1, int(np.sum([t["cg_iterations"] for t in stats])))},
                 "per_step": {"events": [t["events"] for t in stats], "cg_iterations": [t["cg_iterations"] for t in stats]},
-                "ranks_consistent": consistent, "roofline": None, "cpu_baseline": None}
+                "pcg_profile": prof, "ranks_consistent": consistent, "ranks_state_sha256": digests[0][:16], "parity": parity,
+                "roofline": None, "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()

@@ -1,0 +1,44 @@
+"""The slab-partitioned multi-GPU path (persistent distributed PCG over NVLink peer memory, target-sharded
+pairwise sum, slab-owned rate table) against the single-GPU path and the oracle, on real hardware: spawns
+torch.distributed.run at 2 / 4 / 8 ranks (whatever the box has).  Skipped on a single-GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _run(world, workload, steps, oracle, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "check_multi_gpu.py"), "--workload", workload, "--steps", str(steps)]
+    if oracle:
+        cmd.append("--oracle")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    assert "MULTI-GPU PARITY OK" in r.stdout
+    assert "MISMATCH" not in r.stdout
+    if oracle:
+        assert "vs ORACLE" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_matches_single_gpu_and_oracle_100k(world):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run(world, "tiled_100k", 3, True, 29620 + world)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_gpu_matches_single_gpu_1M(world):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run(world, "tiled_1M", 2, False, 29640 + world)
