@@ -67,7 +67,7 @@ EXPORTS = [
     "dkmc_background_potential_sparse", "dkmc_update_CB_edge_sparse", "dkmc_assemble_K", "dkmc_spmv", "dkmc_solve_cg", "dkmc_pcg_profile", "dkmc_ctx_set_legacy_cg",
     "dkmc_poisson_gridless", "dkmc_poisson_gridless_rows", "dkmc_poisson_gridless_begin",
     "dkmc_poisson_gridless_join", "dkmc_ctx_set_pairwise_share", "dkmc_ctx_set_pairwise_cells", "dkmc_ctx_set_pairwise_cutoff", "dkmc_ctx_set_pairwise_incremental", "dkmc_pairwise_incremental_counts",
-    "dkmc_pairwise_pairs_evaluated", "dkmc_build_event_list",
+    "dkmc_pairwise_pairs_evaluated", "dkmc_ctx_set_pairwise_far_field", "dkmc_pairwise_pairs_far", "dkmc_build_event_list",
     "dkmc_inclusive_scan", "dkmc_select_event", "dkmc_execute_kmc_step", "dkmc_kmc_step_continue",
     "dkmc_ctx_set_exact_select", "dkmc_last_event_tables", "dkmc_probe_fp64_tflops", "dkmc_spmv_tile_nnz", "dkmc_dist_unique_id", "dkmc_dist_init",
     "dkmc_dist_finalize", "dkmc_dist_background_potential", "dkmc_dist_p2p_alloc", "dkmc_dist_p2p_open", "dkmc_dist_allgather_rows",
@@ -125,6 +125,8 @@ def load() -> C.CDLL:
         lib.dkmc_ctx_set_pairwise_incremental.argtypes = [vp, ci]
         lib.dkmc_pairwise_incremental_counts.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         lib.dkmc_pairwise_pairs_evaluated.argtypes = [vp, C.POINTER(C.c_longlong)]
+        lib.dkmc_pairwise_pairs_far.argtypes = [vp, C.POINTER(C.c_longlong)]
+        lib.dkmc_ctx_set_pairwise_far_field.argtypes = [vp, C.c_int]
         lib.dkmc_build_event_list.argtypes = [vp, ci, ci, vp, vp, vp, ci] + [vp] * 13
         lib.dkmc_inclusive_scan.argtypes = [vp, C.c_longlong, vp, vp]
         lib.dkmc_select_event.argtypes = [vp, C.c_longlong, vp, cd, C.POINTER(C.c_longlong), C.POINTER(cd)]

@@ -111,6 +111,13 @@ int dkmc_ctx_create(dkmc_ctx **out) {
     DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap_done, cudaEventDisableTiming));
     if (const char *e = getenv("DKMC_LEGACY_CG")) ctx->legacy_cg = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DKMC_PW_SIDE_BPS")) { int v = atoi(e); if (v > 0) ctx->pw_side_blocks_per_sm = v; }
+    if (const char *e = getenv("DKMC_PW_SHARE")) {   // experiments: "blocks_per_sm,threads" of the overlapped pairwise sum
+        int b = 0, t = 0;
+        if (sscanf(e, "%d,%d", &b, &t) == 2 && b >= 1 && b <= 16 && t >= 32 && t <= 256 && t % 32 == 0) {
+            ctx->pw_side_blocks_per_sm = b;
+            ctx->pw_side_threads = t;
+        }
+    }
     *out = ctx;
     return DKMC_OK;
 }

@@ -122,6 +122,21 @@ __device__ __forceinline__ double erfc_fast(double t) {
     return t < kErfcZero ? g * e : 0.0;  // erfc < 1e-305 beyond: contributes nothing at 1e-10
 }
 
+// Far field, t = c r >= kErfcFarT0: erfc(t) / r = exp(-t^2) F(1/t^2) / (c sqrt(pi) r^2) — no square root and
+// no division beyond 1/r^2 (tools/fit_erfcx.py: F by a degree-10 polynomial, 1e-14 relative).  Returns
+// exp(-t^2) F(1/t^2) / r^2; the caller multiplies the sum by 1 / (c sqrt(pi)).  ~40 FP64 instructions per
+// pair instead of ~62 for the general formula.  Exactly 0 from t = kErfcZero on, like erfc_fast.
+__device__ __forceinline__ double erfc_far_over_r(double r2, double c2, double inv_c2) {
+    const double y = rcp_fast(r2);          // 1 / r^2
+    const double t2 = r2 * c2;              // t^2
+    const double sv = y * inv_c2;           // 1 / t^2
+    double f = kErfcFarC[kErfcFarDeg];
+#pragma unroll
+    for (int i = kErfcFarDeg - 1; i >= 0; --i) f = fma(f, sv, kErfcFarC[i]);
+    const double e = exp_neg_fast(fmin(t2, 700.0));
+    return t2 < kErfcZero * kErfcZero ? (f * e) * y : 0.0;
+}
+
 // phi_c[i] = k q_e sum_j q_j erfc(r_ij / (sigma sqrt 2)) / r_ij.  Two targets per thread, sources
 // staged in shared memory, two sources per iteration: four independent FP64 chains per thread keep
 // the FP64 pipe busy with few resident warps (the kernel shares the SMs with the CG), no atomics.
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
     const PwGrid *__restrict__ gp, const int *__restrict__ cell_start, const ChargedSite *__restrict__ src,
     const int *__restrict__ src_idx, const double *__restrict__ sigma_ptr, const double *__restrict__ k_ptr,
     int *tile_counter, int *sm_count, int sm_quota, unsigned sm_quota_linger_ns, unsigned long long *pair_counter,
-    int accumulate, double *out) {
+    int accumulate, int far_on, double *out) {
     __shared__ int s_tile;
     if (sm_count != nullptr) {
         if (threadIdx.x == 0) {
@@ -374,10 +389,14 @@ __global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
     const PwGrid g = *gp;
     const double sigma = *sigma_ptr, kc = *k_ptr;
     const double cscale = 1e-10 / (sigma * sqrt(2.0));
+    const double c2 = cscale * cscale, inv_c2 = 1.0 / c2;
+    const double far_scale = 1.0 / (cscale * 1.7724538509055160273);   // 1 / (c sqrt(pi))
+    // far-field distance: t >= kErfcFarT0 with a margin for the rounding of the box arithmetic
+    const double r_far = far_on ? kErfcFarT0 / cscale * (1.0 + 1e-9) : 1e300, r_far2 = far_on ? r_far * r_far : 1e300;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const int lane = threadIdx.x & 31;
     const int n_tiles = (row_end - row_begin + 63) / 64;   // a tile = the 64 targets of one warp
-    unsigned long long my_pairs = 0;
+    unsigned long long my_pairs = 0, my_far = 0;
 
     while (true) {
         // every warp fetches its own tiles: no CTA-wide barrier, a warp with a short cell walk does
@@ -404,7 +423,8 @@ __global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
         const int cy1 = min(g.ncy - 1, pw_cell_coord(hi[1], g.oy, g.inv_h, g.ncy) + g.reach);
         const int cz0 = max(0, pw_cell_coord(lo[2], g.oz, g.inv_h, g.ncz) - g.reach);
         const int cz1 = min(g.ncz - 1, pw_cell_coord(hi[2], g.oz, g.inv_h, g.ncz) + g.reach);
-        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;      // near field: general formula
+        double fa0 = 0.0, fa1 = 0.0, fb0 = 0.0, fb1 = 0.0;  // far field: sums of q exp(-t^2) F / r^2
 
         auto pair_term = [&](double xi, double yi, double zi, int i, const ChargedSite &s, int sidx) -> double {
             double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
@@ -414,6 +434,64 @@ __global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
             double term = s.q * erfc_fast(r * cscale) * rinv;
             term = (r2 == 0.0) ? s.q * inf : term;   // coincident sites: the reference divides by zero
             return (sidx == i) ? 0.0 : term;         // i != j (potential_solver.cpp:422)
+        };
+        // a far run lies at least r_far from every target of the warp: t >= kErfcFarT0, r > 0, j != i
+        auto far_term = [&](double xi, double yi, double zi, const ChargedSite &s) -> double {
+            double dx = xi - s.x, dy = yi - s.y, dz = zi - s.z;
+            double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            return s.q * erfc_far_over_r(r2, c2, inv_c2);
+        };
+        // the sources [s0, s1) of the sorted list, two per iteration, the next two requested ahead
+        auto near_run = [&](int s0, int s1) {
+            int e = s0;
+            if (e + 1 < s1) {
+                ChargedSite p0 = src[e], p1 = src[e + 1];
+                int j0 = __ldg(src_idx + e), j1 = __ldg(src_idx + e + 1);
+                for (; e + 3 < s1; e += 2) {
+                    const ChargedSite n0 = src[e + 2], n1 = src[e + 3];
+                    const int k0 = __ldg(src_idx + e + 2), k1 = __ldg(src_idx + e + 3);
+                    a0 += pair_term(xa, ya, za, ia, p0, j0);
+                    b0 += pair_term(xb, yb, zb, ib, p0, j0);
+                    a1 += pair_term(xa, ya, za, ia, p1, j1);
+                    b1 += pair_term(xb, yb, zb, ib, p1, j1);
+                    p0 = n0; p1 = n1; j0 = k0; j1 = k1;
+                }
+                a0 += pair_term(xa, ya, za, ia, p0, j0);
+                b0 += pair_term(xb, yb, zb, ib, p0, j0);
+                a1 += pair_term(xa, ya, za, ia, p1, j1);
+                b1 += pair_term(xb, yb, zb, ib, p1, j1);
+                e += 2;
+            }
+            if (e < s1) {
+                const ChargedSite p0 = src[e];
+                const int j0 = __ldg(src_idx + e);
+                a0 += pair_term(xa, ya, za, ia, p0, j0);
+                b0 += pair_term(xb, yb, zb, ib, p0, j0);
+            }
+        };
+        auto far_run = [&](int s0, int s1) {
+            int e = s0;
+            if (e + 1 < s1) {
+                ChargedSite p0 = src[e], p1 = src[e + 1];
+                for (; e + 3 < s1; e += 2) {
+                    const ChargedSite n0 = src[e + 2], n1 = src[e + 3];
+                    fa0 += far_term(xa, ya, za, p0);
+                    fb0 += far_term(xb, yb, zb, p0);
+                    fa1 += far_term(xa, ya, za, p1);
+                    fb1 += far_term(xb, yb, zb, p1);
+                    p0 = n0; p1 = n1;
+                }
+                fa0 += far_term(xa, ya, za, p0);
+                fb0 += far_term(xb, yb, zb, p0);
+                fa1 += far_term(xa, ya, za, p1);
+                fb1 += far_term(xb, yb, zb, p1);
+                e += 2;
+            }
+            if (e < s1) {
+                const ChargedSite p0 = src[e];
+                fa0 += far_term(xa, ya, za, p0);
+                fb0 += far_term(xb, yb, zb, p0);
+            }
         };
 
         for (int cx = cx0; cx <= cx1; ++cx) {
@@ -432,44 +510,40 @@ __global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
                 if (za0 > za1) continue;
                 const int c0 = (cx * g.ncy + cy) * g.ncz;
                 const int s0 = __ldg(cell_start + c0 + za0), s1 = __ldg(cell_start + c0 + za1 + 1);
-                if (va) my_pairs += (unsigned long long)(s1 - s0);
-                if (vb) my_pairs += (unsigned long long)(s1 - s0);
-                int e = s0;
-                if (e + 1 < s1) {
-                    // the next two sources are requested before the current two are evaluated
-                    ChargedSite p0 = src[e], p1 = src[e + 1];
-                    int j0 = __ldg(src_idx + e), j1 = __ldg(src_idx + e + 1);
-                    for (; e + 3 < s1; e += 2) {
-                        const ChargedSite n0 = src[e + 2], n1 = src[e + 3];
-                        const int k0 = __ldg(src_idx + e + 2), k1 = __ldg(src_idx + e + 3);
-                        a0 += pair_term(xa, ya, za, ia, p0, j0);
-                        b0 += pair_term(xb, yb, zb, ib, p0, j0);
-                        a1 += pair_term(xa, ya, za, ia, p1, j1);
-                        b1 += pair_term(xb, yb, zb, ib, p1, j1);
-                        p0 = n0; p1 = n1; j0 = k0; j1 = k1;
-                    }
-                    a0 += pair_term(xa, ya, za, ia, p0, j0);
-                    b0 += pair_term(xb, yb, zb, ib, p0, j0);
-                    a1 += pair_term(xa, ya, za, ia, p1, j1);
-                    b1 += pair_term(xb, yb, zb, ib, p1, j1);
-                    e += 2;
+                const unsigned long long np = (unsigned long long)(s1 - s0) * ((va ? 1 : 0) + (vb ? 1 : 0));
+                my_pairs += np;
+                // the cells of the column that may hold a source closer than r_far to one of the targets take the
+                // general formula; the run below and the run above them the far-field one (warp-uniform)
+                int zn0 = za1 + 1, zn1 = za1;    // empty near range: the whole column is far
+                if (gxy < r_far2) {
+                    const double dzn = sqrt(r_far2 - gxy);
+                    zn0 = max(za0, pw_cell_coord(lo[2] - dzn, g.oz, g.inv_h, g.ncz));
+                    zn1 = min(za1, pw_cell_coord(hi[2] + dzn, g.oz, g.inv_h, g.ncz));
+                    if (zn0 > zn1) { zn0 = za1 + 1; zn1 = za1; }
                 }
-                if (e < s1) {
-                    const ChargedSite p0 = src[e];
-                    const int j0 = __ldg(src_idx + e);
-                    a0 += pair_term(xa, ya, za, ia, p0, j0);
-                    b0 += pair_term(xb, yb, zb, ib, p0, j0);
+                if (zn0 > za1) {
+                    far_run(s0, s1);
+                    my_far += np;
+                } else {
+                    const int n0 = __ldg(cell_start + c0 + zn0), n1 = __ldg(cell_start + c0 + zn1 + 1);
+                    far_run(s0, n0);
+                    near_run(n0, n1);
+                    far_run(n1, s1);
+                    my_far += (unsigned long long)((n0 - s0) + (s1 - n1)) * ((va ? 1 : 0) + (vb ? 1 : 0));
                 }
             }
         }
-        // rinv is in 1/Angstrom: 1e10 converts to 1/m
+        // rinv is in 1/Angstrom: 1e10 converts to 1/m; the far-field sums carry the factor 1 / (c sqrt(pi))
         // accumulate: the sources are charge DIFFERENCES and out holds the previous potential (8f-2)
-        if (va) { const double v = (a0 + a1) * (kc * kElementaryCharge * 1e10); out[ia] = accumulate ? out[ia] + v : v; }
-        if (vb) { const double v = (b0 + b1) * (kc * kElementaryCharge * 1e10); out[ib] = accumulate ? out[ib] + v : v; }
+        if (va) { const double v = ((a0 + a1) + (fa0 + fa1) * far_scale) * (kc * kElementaryCharge * 1e10); out[ia] = accumulate ? out[ia] + v : v; }
+        if (vb) { const double v = ((b0 + b1) + (fb0 + fb1) * far_scale) * (kc * kElementaryCharge * 1e10); out[ib] = accumulate ? out[ib] + v : v; }
     }
-    if (pair_counter != nullptr) {   // pairs evaluated, for the roofline
-        for (int o = 16; o > 0; o >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o);
-        if (lane == 0) atomicAdd(pair_counter, my_pairs);
+    if (pair_counter != nullptr) {   // pairs evaluated (all | by the far-field formula), for the roofline
+        for (int o = 16; o > 0; o >>= 1) {
+            my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, o);
+            my_far += __shfl_xor_sync(0xffffffffu, my_far, o);
+        }
+        if (lane == 0) { atomicAdd(pair_counter, my_pairs); atomicAdd(pair_counter + 1, my_far); }
     }
 }
 
@@ -508,7 +582,7 @@ static int pairwise_bin_cells(dkmc_ctx *ctx, int N, const double *d_x, const dou
     double *box;          // [6 * kBoxBlocks] partial min/max | PwGrid
     int *cells;           // cell_count[kPwMaxCells + 1] | cell_start[kPwMaxCells + 1] | cell_of[N]
     int rc;
-    const size_t box_doubles = 6 * kBoxBlocks + (sizeof(PwGrid) + 7) / 8 + 2;
+    const size_t box_doubles = 6 * kBoxBlocks + (sizeof(PwGrid) + 7) / 8 + 4;
     if ((rc = ensure<double>(ctx, S_PW_BOX, box_doubles, &box))) return rc;
     if ((rc = ensure<int>(ctx, S_PW_CELLS, (size_t)2 * (kPwMaxCells + 1) + (size_t)N, &cells))) return rc;
     if ((rc = ensure<ChargedSite>(ctx, S_PW_SRC2, (size_t)N, &out->src))) return rc;
@@ -524,7 +598,7 @@ static int pairwise_bin_cells(dkmc_ctx *ctx, int N, const double *d_x, const dou
         gc.d_x = d_x; gc.d_sigma = d_sigma; gc.N = N; gc.box = box; gc.cutoff_sigmas = ctx->pw_cutoff_sigmas;
     }
     DKMC_CUDA(cudaMemsetAsync(cell_count, 0, (kPwMaxCells + 1) * sizeof(int), ctx->stream));
-    DKMC_CUDA(cudaMemsetAsync(pair_counter, 0, sizeof(unsigned long long), ctx->stream));
+    DKMC_CUDA(cudaMemsetAsync(pair_counter, 0, 2 * sizeof(unsigned long long), ctx->stream));
     int grid_n = ceil_div(N, 256);
     if (grid_n > 1024) grid_n = 1024;
     DKMC_LAUNCH(ctx, pw_cell_count_kernel, grid_n, 256, 0, total, src, grid, cell_of, cell_count);
@@ -591,7 +665,7 @@ static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm
         static const int pad_smem = [] { const char *e = getenv("DKMC_PW_PAD_SMEM"); return e ? atoi(e) : 16384; }();
         DKMC_LAUNCH_ON(ctx, stream, pairwise_cells_kernel, grid, threads, pad_smem, row_begin, row_end, d_x, d_y, d_z, cells->grid,
                        cells->cell_start, cells->src, cells->src_idx, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm,
-                       pw_linger_ns(), cells->pair_counter, accumulate, d_out);
+                       pw_linger_ns(), cells->pair_counter, accumulate, ctx->pw_far_field, d_out);
         if (shared_sms && pw_gate_enabled()) DKMC_LAUNCH(ctx, pw_gate_kernel, 1, 1, 0, sm_count + 256, grid);
         return DKMC_OK;
     }
@@ -776,6 +850,25 @@ int dkmc_pairwise_pairs_evaluated(dkmc_ctx *ctx, long long *pairs) {
     DKMC_CUDA(cudaMemcpyAsync(&h, pc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
     *pairs = (long long)h;
+    return DKMC_OK;
+}
+
+int dkmc_pairwise_pairs_far(dkmc_ctx *ctx, long long *pairs) {
+    DKMC_REQUIRE(ctx != nullptr && pairs != nullptr, "ctx/pairs");
+    *pairs = -1;
+    if (!ctx->slot_ptr[S_PW_BOX]) return DKMC_OK;
+    const double *box = static_cast<const double *>(ctx->slot_ptr[S_PW_BOX]);
+    const unsigned long long *pc = reinterpret_cast<const unsigned long long *>(box + 6 * 256 + (sizeof(PwGrid) + 7) / 8);
+    unsigned long long h = 0;
+    DKMC_CUDA(cudaMemcpyAsync(&h, pc + 1, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    *pairs = (long long)h;
+    return DKMC_OK;
+}
+
+int dkmc_ctx_set_pairwise_far_field(dkmc_ctx *ctx, int on) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    ctx->pw_far_field = on ? 1 : 0;
     return DKMC_OK;
 }
 

@@ -10,8 +10,10 @@
 //     beta = gamma / gamma_old ; alpha = gamma / (delta - beta gamma / alpha_old)
 // M^-1 = D^-1 + W E^-1 W^T (Jacobi + one coarse unknown per uncharged-vacancy cluster, solver.cu).  The cluster
 // sums W^T r follow the same recurrences (W^T s = W^T w + beta W^T s, W^T r -= alpha W^T s) from W^T w, which is
-// computed beside the SpMV and travels in the same reduction — so clusters may straddle slab faces and the
-// preconditioner costs no extra synchronisation.
+// computed beside the SpMV.  A cluster whose members all lie in one rank's rows (almost all of them) is that
+// rank's private business: its sum is read back from local memory after the barrier.  Only the clusters that
+// straddle a slab face travel in the reduction, beside the two scalars — so the preconditioner costs no extra
+// synchronisation and a few words of NVLink traffic.
 //
 // An iteration is two phases separated by grid barriers:
 //   V  vector phase over the own rows (p, s, x, r, u; gamma partial); boundary rows of u are stored straight
@@ -33,7 +35,7 @@
 struct PcgSync {
     unsigned int arrive_h, arrive_r;   // arrival counters of the two barrier kinds (reset by the last arriver)
     unsigned long long gen_h;          // local release of barrier H: the halo sequence number reached
-    unsigned long long pad;
+    unsigned int n_global, pad;        // clusters that straddle a slab face (length of gl_list; zeroed per launch)
 };
 
 struct PcgArgs {
@@ -44,7 +46,10 @@ struct PcgArgs {
     double *x, *r, *w, *p, *s;           // full-length vectors; only the own rows [ra, rb) are touched
     Precond P;                           // cluster tables (pos may be null: plain Jacobi)
     double *cs, *cr;                     // [2][n_cl] cluster-sum recurrences W^T s, W^T r (replicated)
-    double *payload;                     // [4 + 2 n_cl] this rank's contribution to a reduction
+    double *payload;                     // [4 + 2 n_cl] this rank's cluster sums (entry 4 + s; b-sums at 4 + n_cl + s)
+    int *cl_kind;                        // [n_cl] at a cluster's first position: 0 not mine, 1 all members mine, 2 straddles ranks
+    int *gl_list;                        // [n_cl] first positions of the straddling clusters (any order)
+    int row_end_all[DKMC_MAX_RANKS];     // last row + 1 of every rank (rank of a row)
     double *partials;                    // [3][gridDim] CTA partial sums
     PcgSync *sync;
     CgScalars *sc;
@@ -112,12 +117,18 @@ __device__ __forceinline__ double pcg_ll_load(const P2pPeers &P, int buf, int q,
     }
     return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
 }
-// sum over the ranks (in rank order) of entry j of reduction `seq`
+// sum over the ranks (in rank order) of entry j of reduction `seq` — one system-scope round trip per rank: only
+// for the few clusters that straddle ranks (the scalars of a reduction are polled by one thread per rank)
 __device__ __forceinline__ double pcg_reduced(const P2pPeers &P, unsigned long long rseq, int j, int *err) {
     const int buf = (int)(rseq & 1ull);
     double acc = 0.0;
     for (int q = 0; q < P.world; ++q) acc += pcg_ll_load(P, buf, q, j, (unsigned int)rseq, err);
     return acc;
+}
+// the sum over cluster s0 (first position) of the latest reduction: private clusters from local memory
+__device__ __forceinline__ double pcg_cluster_sum(const PcgArgs &a, unsigned long long rseq, int s0, int off, int *err) {
+    if (__ldcg(a.cl_kind + s0) == 1) return __ldcg(a.payload + 4 + off + s0);
+    return pcg_reduced(a.peers, rseq, 4 + off + s0, err);
 }
 
 __device__ __forceinline__ bool pcg_push(const P2pHalo &H, const P2pPeers &P, int i, double v) {
@@ -167,11 +178,12 @@ __device__ __forceinline__ void pcg_barrier_halo(const PcgArgs &a, unsigned long
 
 // Barrier R + all-reduce.  On entry every CTA has written its `nparts` partial sums (partials[q * grid + cta])
 // and the cluster warps their entries of a.payload[4 ..).  The last CTA to arrive adds the partials in index
-// order and sends [sums | cluster entries] to every rank (LL words); every CTA then waits for the four leading
-// words of every rank — this rank's own words double as the local barrier release — and adds them in rank
-// order: out[0 .. 3] = global sums.  The cluster entries are read where they are needed (pcg_reduced).
-// K = payload length.  Returns true if a wait timed out somewhere on this GPU.
-__device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned long long rseq, int nparts, int K,
+// order and sends [sums | entries of the straddling clusters] to every rank (LL words); every CTA then waits
+// for the four leading words of every rank — this rank's own words double as the local barrier release — one
+// thread per (entry, rank), all polls in flight together, and adds them in rank order: out[0 .. 3] = global
+// sums.  The cluster entries are read where they are needed (pcg_cluster_sum).  with_b: the straddling
+// clusters also send their second array (set-up).  Returns true if a wait timed out on this GPU.
+__device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned long long rseq, int nparts, bool with_b,
                                                    double *out, double *sh) {
     const P2pPeers &P = a.peers;
     __shared__ bool s_last;
@@ -179,8 +191,10 @@ __device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned lo
     __shared__ int s_err;
     const int buf = (int)(rseq & 1ull);
     const unsigned int seq = (unsigned int)rseq;
+    const int n = a.n_cl;
     __syncthreads();
     if (threadIdx.x == 0) {
+        s_err = 0;
         __threadfence();
         s_last = (atomicAdd(&a.sync->arrive_r, 1u) == gridDim.x - 1);
     }
@@ -202,33 +216,48 @@ __device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned lo
         }
         if (threadIdx.x == 0) { s_loc[3] = 0.0; a.sync->arrive_r = 0u; }
         __syncthreads();
-        // remote ranks first (their words are self-validating), the cluster entries of this rank, and last —
-        // behind a fence — this rank's four leading words: whoever reads them may read everything written
-        // on this GPU before the barrier
+        // remote ranks first (their words are self-validating), the straddling clusters' entries of this rank,
+        // and last — behind a fence — this rank's four leading words: whoever reads them may read everything
+        // written on this GPU before the barrier
+        const int ng = P.world > 1 ? (int)__ldcg(&a.sync->n_global) : 0;
+        const int per = with_b ? 2 : 1, K = 4 + per * ng;
         for (int q = 0; q < P.world; ++q) {
-            if (q == P.rank) continue;
             unsigned long long *slot = pcg_slot(P, q, buf, P.rank);
-            for (int j = threadIdx.x; j < K; j += blockDim.x) pcg_ll_store(slot, j, j < 4 ? s_loc[j] : __ldcg(a.payload + j), seq);
+            for (int e = threadIdx.x; e < K; e += blockDim.x) {
+                if (e < 4) {
+                    if (q != P.rank) pcg_ll_store(slot, e, s_loc[e], seq);
+                } else {
+                    const int gi = (e - 4) / per, second = (e - 4) - gi * per;
+                    const int j = 4 + second * n + __ldcg(a.gl_list + gi);
+                    pcg_ll_store(slot, j, __ldcg(a.payload + j), seq);
+                }
+            }
         }
-        unsigned long long *mine = pcg_slot(P, P.rank, buf, P.rank);
-        for (int j = 4 + threadIdx.x; j < K; j += blockDim.x) pcg_ll_store(mine, j, __ldcg(a.payload + j), seq);
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
+            unsigned long long *mine = pcg_slot(P, P.rank, buf, P.rank);
             for (int j = 0; j < 4; ++j) pcg_ll_store(mine, j, s_loc[j], seq);
         }
     }
-    if (threadIdx.x == 0) s_err = 0;
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        int err = 0;
-        out[threadIdx.x] = pcg_reduced(P, rseq, threadIdx.x, &err);
-        __threadfence();   // acquire side of the local barrier (fence - relaxed store / relaxed load - fence)
-        if (err) { s_err = err; a.sc->pad = err; }
+    // one thread per (entry, rank): all polls in flight together; sums in rank order
+    double *s_w = sh;   // [world][4] staged words (world <= 8 here; larger worlds loop)
+    for (int q0 = 0; q0 < P.world; q0 += 8) {
+        const int e = (int)threadIdx.x & 3, q = q0 + ((int)threadIdx.x >> 2);
+        if (threadIdx.x < 32 && q < P.world) {
+            int err = 0;
+            s_w[threadIdx.x] = pcg_ll_load(P, buf, q, e, seq, &err);
+            __threadfence();   // acquire side of the local barrier (fence - relaxed store / relaxed load - fence)
+            if (err) { s_err = err; a.sc->pad = err; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double acc = q0 == 0 ? 0.0 : out[threadIdx.x];
+            for (int u = 0; u < 8 && q0 + u < P.world; ++u) acc += s_w[4 * u + threadIdx.x];
+            out[threadIdx.x] = acc;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_err == 0) s_err = *reinterpret_cast<volatile int *>(&a.sc->pad);   // a timeout elsewhere on this GPU
-    __syncthreads();
     return s_err != 0;
 }
 
@@ -333,7 +362,8 @@ __device__ __forceinline__ void pcg_cluster_rows(const PcgArgs &a, const double 
     const int G = (int)gridDim.x;
     for (int s = (G - 1 - (int)blockIdx.x) + (int)(threadIdx.x >> 5) * G; s < n; s += G * wpb) {
         double acc = 0.0, accb = 0.0;
-        if (__ldg(a.P.seg_start + s) == s) {
+        if (__ldg(a.P.seg_start + s) != s || __ldcg(a.cl_kind + s) == 0) continue;   // not a first position / no member here
+        {
             const int len = __ldg(a.P.seg_len + s);
             for (int k = 0; k < len; ++k) {
                 const int row = __ldg(a.P.mem_row + s + k);
@@ -389,12 +419,25 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
             g[i] = v;
             pushed |= pcg_push(a.halo, P, i, v);
         }
+        // clusters: whose business are they?  Members are sorted by row inside a cluster, so the ranks of the
+        // first and the last member decide: both mine -> private (1); same other rank -> not mine (0); else the
+        // cluster straddles a slab face (2) and its sums travel in the reductions (same verdict on every rank)
+        for (int s = cta * B + tid; s < n; s += G * B)
+            if (__ldg(a.P.seg_start + s) == s) {
+                const int first = __ldg(a.P.mem_row + s), last = __ldg(a.P.mem_row + s + __ldg(a.P.seg_len + s) - 1);
+                int qf = 0, ql = 0;
+                while (qf < P.world - 1 && first >= a.row_end_all[qf]) ++qf;
+                while (ql < P.world - 1 && last >= a.row_end_all[ql]) ++ql;
+                const int kind = qf != ql ? 2 : (qf == P.rank ? 1 : 0);
+                a.cl_kind[s] = kind;
+                if (kind == 2) a.gl_list[atomicAdd(&a.sync->n_global, 1u)] = s;
+            }
         pcg_barrier_halo(a, a.hseq0 + 1, pushed);
     }
     // ---- init 1: r = b - A x; cluster sums of r and of b
     pcg_spmv_tiles<2>(a, g, a.r, prod);
     if (clustered) pcg_cluster_rows<2>(a, g);
-    pcg_barrier_reduce(a, a.rseq0 + 1, 0, 4 + 2 * n, s_out, red);
+    pcg_barrier_reduce(a, a.rseq0 + 1, 0, true, s_out, red);
     // ---- init 2: u = M^-1 r (into the window), gamma and b.M^-1 b partials, recurrence state
     {
         const unsigned long long rs_ = a.rseq0 + 1;
@@ -408,8 +451,8 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
             if (sp >= 0) {
                 const int s0 = __ldg(a.P.seg_start + sp);
                 const double we = __ldg(a.P.w + s0);
-                un += we * pcg_reduced(P, rs_, 4 + s0, &lerr);
-                zb += we * pcg_reduced(P, rs_, 4 + n + s0, &lerr);
+                un += we * pcg_cluster_sum(a, rs_, s0, 0, &lerr);
+                zb += we * pcg_cluster_sum(a, rs_, s0, n, &lerr);
             }
             g[i] = un;
             pushed |= pcg_push(a.halo, P, i, un);
@@ -417,7 +460,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
             lbb += bi * zb;
         }
         for (int s = cta * B + tid; s < n; s += G * B)
-            if (__ldg(a.P.seg_start + s) == s) { a.cr[s] = pcg_reduced(P, rs_, 4 + s, &lerr); a.cs[s] = 0.0; }
+            if (__ldg(a.P.seg_start + s) == s && __ldcg(a.cl_kind + s) != 0) { a.cr[s] = pcg_cluster_sum(a, rs_, s, 0, &lerr); a.cs[s] = 0.0; }
         if (lerr) a.sc->pad = lerr;
         lg = block_sum(lg, red);
         __syncthreads();
@@ -431,7 +474,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
         if (clustered) pcg_cluster_rows<1>(a, g);
         ld = block_sum(ld, red);
         if (tid == 0) a.partials[(size_t)G + cta] = ld;
-        const bool err = pcg_barrier_reduce(a, a.rseq0 + 2, 3, 4 + n, s_out, red);
+        const bool err = pcg_barrier_reduce(a, a.rseq0 + 2, 3, false, s_out, red);
         if (tid == 0) {
             const double gamma = s_out[0], delta = s_out[1], bb = s_out[2];
             st.gamma = gamma; st.bb = bb;
@@ -472,7 +515,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
                 double un = ri * di;
                 if (sp >= 0) {
                     const int s0 = __ldg(a.P.seg_start + sp);
-                    const double csn = pcg_reduced(P, rs_, 4 + s0, &lerr) + beta * cs_old[s0];
+                    const double csn = pcg_cluster_sum(a, rs_, s0, 0, &lerr) + beta * cs_old[s0];
                     un += __ldg(a.P.w + s0) * (cr_old[s0] - alpha * csn);
                 }
                 g[i] = un;
@@ -480,8 +523,8 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
                 lg += ri * un;
             }
             for (int s = cta * B + tid; s < n; s += G * B)
-                if (__ldg(a.P.seg_start + s) == s) {
-                    const double csn = pcg_reduced(P, rs_, 4 + s, &lerr) + beta * cs_old[s];
+                if (__ldg(a.P.seg_start + s) == s && __ldcg(a.cl_kind + s) != 0) {
+                    const double csn = pcg_cluster_sum(a, rs_, s, 0, &lerr) + beta * cs_old[s];
                     cs_new[s] = csn;
                     cr_new[s] = cr_old[s] - alpha * csn;
                 }
@@ -502,7 +545,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
             if (tid == 0) a.partials[(size_t)G + cta] = ld;
             PCG_PROF(4);
             if (PROF && cta_prof) { const long long now = pcg_now(); cp_s += now - cp_t; cp_t = now; }
-            const bool err = pcg_barrier_reduce(a, a.rseq0 + 3 + it, 2, 4 + n, s_out, red);
+            const bool err = pcg_barrier_reduce(a, a.rseq0 + 3 + it, 2, false, s_out, red);
             if (PROF && cta_prof) cp_w += pcg_now() - cp_t;
             PCG_PROF(5);
             if (tid == 0) {

@@ -985,6 +985,7 @@ static int pcg_ctas_per_sm(dkmc_ctx *ctx, int *variant) {
 
 struct PcgGeometry {
     int ra, rb, t0, t1, n_cl;
+    int row_end_all[DKMC_MAX_RANKS];
     P2pPeers peers;
     P2pHalo halo;
     unsigned long long *pseq_r, *pseq_h;
@@ -1003,9 +1004,12 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
     if ((rc = ensure<double>(ctx, S_CG_S, (size_t)m, &s_vec))) return rc;
     if ((rc = ensure<double>(ctx, S_CL_REC, (size_t)4 * n + 8, &rec))) return rc;
     if ((rc = ensure<double>(ctx, S_DIST_RED, (size_t)4 + 2 * (size_t)n + 8, &payload))) return rc;
+    int *clk;
+    if ((rc = ensure<int>(ctx, S_PCG_CLK, (size_t)2 * n + 8, &clk))) return rc;
     const bool fresh = ctx->slot_ptr[S_PCG_SYNC] == nullptr;
     if ((rc = ensure<PcgSync>(ctx, S_PCG_SYNC, 1, &sync))) return rc;
     if (fresh) DKMC_CUDA(cudaMemsetAsync(sync, 0, sizeof(PcgSync), ctx->stream));
+    DKMC_CUDA(cudaMemsetAsync(&sync->n_global, 0, sizeof(unsigned int), ctx->stream));
     static const bool want_prof = getenv("DKMC_PCG_PROF") != nullptr;
     long long *prof = nullptr;
     if (want_prof) {
@@ -1018,6 +1022,8 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
     a.x = d_x; a.r = w.r[0]; a.w = w.Ap; a.p = w.p; a.s = s_vec;
     a.P = w.P;
     a.cs = rec; a.cr = rec + 2 * (size_t)n;
+    a.cl_kind = clk; a.gl_list = clk + n + 4;
+    for (int q = 0; q < DKMC_MAX_RANKS; ++q) a.row_end_all[q] = geo.row_end_all[q];
     a.payload = payload; a.partials = w.partials; a.sync = sync; a.sc = w.sc; a.tol = tol;
     a.rseq0 = *geo.pseq_r; a.hseq0 = *geo.pseq_h;
     a.peers = geo.peers; a.halo = geo.halo; a.prof = prof;
@@ -1095,6 +1101,7 @@ static int run_pcg_persistent_single(dkmc_ctx *ctx, int m, int nnz, const int *d
     PcgGeometry geo;
     memset(&geo, 0, sizeof(geo));
     geo.ra = 0; geo.rb = m; geo.t0 = 0; geo.t1 = w.num_tiles; geo.n_cl = w.n_cl;
+    geo.row_end_all[0] = m;
     geo.peers = sw->peers;
     geo.pseq_r = &sw->pseq_r; geo.pseq_h = &sw->pseq_h;
     return run_pcg_persistent(ctx, m, d_row_ptr, d_col, d_val, d_b, d_x, w, geo, tol, max_iter, iters_out, converged, bb_out);
@@ -1425,6 +1432,7 @@ static int dist_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const i
         PcgGeometry geo;
         memset(&geo, 0, sizeof(geo));
         geo.ra = d.ra; geo.rb = d.rb; geo.t0 = d.t0; geo.t1 = d.t1; geo.n_cl = n;
+        for (int q = 0; q < ds->world; ++q) geo.row_end_all[q] = d.plan->row_end[q];
         geo.peers = ds->peers;
         fill_halo_desc(d.plan, &geo.halo);
         geo.pseq_r = &ds->pseq_r; geo.pseq_h = &ds->pseq_h;

@@ -195,6 +195,14 @@ int dkmc_ctx_set_pairwise_cells(dkmc_ctx *ctx, int on);
  * it as a separate variant, never as the headline. */
 int dkmc_ctx_set_pairwise_cutoff(dkmc_ctx *ctx, double cutoff_sigmas);
 int dkmc_pairwise_pairs_evaluated(dkmc_ctx *ctx, long long *pairs);
+/* Far field of the cell-list kernel (default on = 1).  A run of sources that lies at least 4 sigma sqrt 2
+ * (19.8 A at the shipped sigma) from every target of a warp is evaluated as
+ * erfc(t) / r = exp(-t^2) F(1/t^2) / (c sqrt(pi) r^2), t = c r — the same function (F by a polynomial fitted
+ * to 1e-14 relative, tools/fit_erfcx.py) without the square root and the second division: ~40 instead of
+ * ~62 FP64 instructions per pair.  on = 0: every pair takes the general formula (test hook).
+ * dkmc_pairwise_pairs_far: pairs the last cell-list sum evaluated by the far-field formula (-1: none yet). */
+int dkmc_ctx_set_pairwise_far_field(dkmc_ctx *ctx, int on);
+int dkmc_pairwise_pairs_far(dkmc_ctx *ctx, long long *pairs);
 /* OPT-IN incremental update, default 0 = off.  Between two KMC steps only the sites
  * touched by executed events change charge, so phi_c(new) = phi_c(old) + sum over the CHANGED sites of
  * (q_new - q_old) * kernel: O(N * n_changed) instead of O(N * n_charged).  With refresh_every = R > 0

@@ -575,7 +575,7 @@ def test_persistent_pcg_matches_per_op_pcg(cell_sim, torch):
 
 def test_potential_overlap_matches_serial(cell_sim, O, torch):
     """pairwise sum on the side stream concurrently with the CG == the two run one after the other;
-    and both within 1e-10 of the oracle on the cell-ordered device (window-staged SpMV inside the CG)"""
+    and both within 1e-10 of the oracle on the cell-ordered device"""
     p, dev, sim, buf, nc = cell_sim
     Vd = 10.0
     buf.site_potential_boundary.zero_()
@@ -585,7 +585,10 @@ def test_potential_overlap_matches_serial(cell_sim, O, torch):
     o2 = dev.updatePotential(buf, p, Vd, n_contact=nc, overlap=True)
     assert o1["cg_converged"] and o2["cg_converged"]
     assert torch.equal(c1, buf.site_potential_charge)
-    assert torch.equal(b1, buf.site_potential_boundary)
+    # the persistent PCG sizes its grid by what is resident beside the pairwise CTAs, so the partial sums of
+    # its reductions are grouped differently in the two runs: same solution to rounding, not the same bits
+    b2 = buf.site_potential_boundary
+    assert float((b1 - b2).abs().max()) <= 1e-12 * float(b1.abs().max())
     nb = dev.neigh_idx.reshape(dev.N, -1)
     q = buf.site_charge.cpu().numpy()
     ref, _ = O.background_potential(nb, nc, nc, dev.site_element, q, p.metals, p.high_G, p.low_G, Vd, refine=3)
