@@ -51,7 +51,7 @@ enum Slot : int {
     S_SP_CNT, S_SCAN_BLOCK,
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
-    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_S, S_CL_REC, S_PCG_SYNC, S_PCG_PROF, S_PCG_CLK, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
+    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_S, S_CL_REC, S_PCG_SYNC, S_PCG_SYNC2, S_PCG_PROF, S_PCG_CLK, S_CG_PZ, S_CG_PN, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
     S_NB_HOSTPOS, S_NB_HOSTTAB, S_PW_PREVQ, S_PW_DQ, S_SNAP_STAGE, S_EV_NZROWS, S_EV_BATCHSUM,
     S_LAST
 };
@@ -110,6 +110,7 @@ struct dkmc_ctx {
         const int *d_charge = nullptr;
         double *d_out = nullptr;
     } pw_pending;
+    int pcg_pipelined = -1;          // persistent PCG: pipelined recurrences (one synchronisation per iteration); -1 = on several GPUs
     int pw_far_field = 1;            // cell-list kernel: far-field formula for the runs beyond t = kErfcFarT0
     int pw_use_cells = 1;            // skip sources beyond the distance where erfc is exactly 0 (non-periodic devices)
     struct { const double *d_x = nullptr, *d_sigma = nullptr; const void *box = nullptr; int N = 0; double cutoff_sigmas = 0.0; } pw_grid;

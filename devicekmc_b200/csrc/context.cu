@@ -110,6 +110,7 @@ int dkmc_ctx_create(dkmc_ctx **out) {
     DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap_staged, cudaEventDisableTiming));
     DKMC_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap_done, cudaEventDisableTiming));
     if (const char *e = getenv("DKMC_LEGACY_CG")) ctx->legacy_cg = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("DKMC_PCG_PIPELINED")) ctx->pcg_pipelined = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DKMC_PW_SIDE_BPS")) { int v = atoi(e); if (v > 0) ctx->pw_side_blocks_per_sm = v; }
     if (const char *e = getenv("DKMC_PW_SHARE")) {   // experiments: "blocks_per_sm,threads" of the overlapped pairwise sum
         int b = 0, t = 0;
@@ -246,6 +247,9 @@ void dkmc_default_solver_opts(dkmc_solver_opts *o) {
     o->cluster_precond = 1;
     o->refine_tol = 1e-6;
     o->est_tol = 1e-13;
+    // experiments only
+    if (const char *e = getenv("DKMC_REL_TOL")) { double v = atof(e); if (v > 0.0) o->rel_tol = v; }
+    if (const char *e = getenv("DKMC_REFINE_TOL")) { double v = atof(e); if (v > 0.0) o->refine_tol = v; }
 }
 
 }  // extern "C"

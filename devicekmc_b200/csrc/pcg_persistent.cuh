@@ -36,6 +36,10 @@ struct PcgSync {
     unsigned int arrive_h, arrive_r;   // arrival counters of the two barrier kinds (reset by the last arriver)
     unsigned long long gen_h;          // local release of barrier H: the halo sequence number reached
     unsigned int n_global, pad;        // clusters that straddle a slab face (length of gl_list; zeroed per launch)
+    unsigned long long gen_r;          // local release of barrier R: the reduction sequence number reached
+    double sums[2][4];                 // the reduced scalars of reduction rseq, double-buffered by its parity
+    double loc[2][4];                  // pipelined PCG: this rank's own sums of reduction rseq (for whoever completes it)
+    unsigned int arrive_s, pad2;       // pipelined PCG: arrivals at the end of the SpMV phase (the first completes the reduction)
 };
 
 struct PcgArgs {
@@ -50,6 +54,8 @@ struct PcgArgs {
     int *cl_kind;                        // [n_cl] at a cluster's first position: 0 not mine, 1 all members mine, 2 straddles ranks
     int *gl_list;                        // [n_cl] first positions of the straddling clusters (any order)
     int row_end_all[DKMC_MAX_RANKS];     // last row + 1 of every rank (rank of a row)
+    double *z, *nvec, *g2;               // pipelined PCG only: z, n = A m, and the second gather buffer (own window + g2_off)
+    size_t g2_off;                       // byte offset of the second gather buffer inside every rank's window
     double *partials;                    // [3][gridDim] CTA partial sums
     PcgSync *sync;
     CgScalars *sc;
@@ -145,7 +151,9 @@ __device__ __forceinline__ bool pcg_push(const P2pHalo &H, const P2pPeers &P, in
 // and so are the neighbours' boundary rows in this rank's window.
 __device__ __forceinline__ void pcg_barrier_halo(const PcgArgs &a, unsigned long long hseq, bool pushed) {
     const P2pPeers &P = a.peers;
+    __shared__ bool s_last_h;
     (void)pushed;
+    const int buf = kPcgFlagH + (int)(hseq & 1ull);
     __syncthreads();
     if (threadIdx.x == 0) {
         // gpu scope is enough also for the rows this CTA stored into the neighbours' windows: the chain
@@ -153,14 +161,26 @@ __device__ __forceinline__ void pcg_barrier_halo(const PcgArgs &a, unsigned long
         // ld.acquire.sys is a causality chain in the PTX memory model, and system-wide fences in every CTA are
         // what made these exchanges slow (15-20 us per barrier, measured)
         __threadfence();
-        const unsigned int t = atomicAdd(&a.sync->arrive_h, 1u);
-        const int buf = kPcgFlagH + (int)(hseq & 1ull);
-        if (t == gridDim.x - 1) {
-            a.sync->arrive_h = 0u;
+        s_last_h = atomicAdd(&a.sync->arrive_h, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last_h) {
+        // the local release and the neighbours' flags leave from different warps: a system-scope release costs
+        // microseconds, and nothing orders the three stores among themselves
+        const int wid = (int)threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0 && wid <= a.halo.n_send && wid < (int)blockDim.x / 32) {
             __threadfence();
-            for (int sgm = 0; sgm < a.halo.n_send; ++sgm) st_release_sys(p2p_flag(P, a.halo.send_peer[sgm], buf, P.rank), hseq);
-            st_release_gpu(&a.sync->gen_h, hseq);
+            if (wid == 0) {
+                a.sync->arrive_h = 0u;
+                st_release_gpu(&a.sync->gen_h, hseq);
+                for (int sgm = (int)blockDim.x / 32 - 1; sgm < a.halo.n_send; ++sgm)   // more neighbours than warps (never on x-slabs)
+                    st_release_sys(p2p_flag(P, a.halo.send_peer[sgm], buf, P.rank), hseq);
+            } else {
+                st_release_sys(p2p_flag(P, a.halo.send_peer[wid - 1], buf, P.rank), hseq);
+            }
         }
+    }
+    if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (ld_relaxed_gpu(&a.sync->gen_h) < hseq)
             if (clock64() - t0 > kP2pTimeoutCycles) { a.sc->pad = 2; break; }
@@ -178,11 +198,13 @@ __device__ __forceinline__ void pcg_barrier_halo(const PcgArgs &a, unsigned long
 
 // Barrier R + all-reduce.  On entry every CTA has written its `nparts` partial sums (partials[q * grid + cta])
 // and the cluster warps their entries of a.payload[4 ..).  The last CTA to arrive adds the partials in index
-// order and sends [sums | entries of the straddling clusters] to every rank (LL words); every CTA then waits
-// for the four leading words of every rank — this rank's own words double as the local barrier release — one
-// thread per (entry, rank), all polls in flight together, and adds them in rank order: out[0 .. 3] = global
-// sums.  The cluster entries are read where they are needed (pcg_cluster_sum).  with_b: the straddling
-// clusters also send their second array (set-up).  Returns true if a wait timed out on this GPU.
+// order, sends [sums | entries of the straddling clusters] to every other rank (LL words), collects the other
+// ranks' sums (one thread per (entry, rank), all polls in flight together), adds them in rank order — identical
+// bits on all ranks — and releases the local barrier with the result.  Everybody else polls ONE local word with
+// ONE thread: with every CTA polling the LL words themselves (the first version) thousands of system-scope
+// loads per round queued on a single L2 line, and the barrier cost 9 us on one GPU and 16-20 us on four.
+// out[0 .. 3] = global sums.  The straddling clusters' entries are read where they are needed
+// (pcg_cluster_sum).  with_b: they also send their second array (set-up).  Returns true after a timeout.
 __device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned long long rseq, int nparts, bool with_b,
                                                    double *out, double *sh) {
     const P2pPeers &P = a.peers;
@@ -216,48 +238,61 @@ __device__ __forceinline__ bool pcg_barrier_reduce(const PcgArgs &a, unsigned lo
         }
         if (threadIdx.x == 0) { s_loc[3] = 0.0; a.sync->arrive_r = 0u; }
         __syncthreads();
-        // remote ranks first (their words are self-validating), the straddling clusters' entries of this rank,
-        // and last — behind a fence — this rank's four leading words: whoever reads them may read everything
-        // written on this GPU before the barrier
-        const int ng = P.world > 1 ? (int)__ldcg(&a.sync->n_global) : 0;
-        const int per = with_b ? 2 : 1, K = 4 + per * ng;
-        for (int q = 0; q < P.world; ++q) {
-            unsigned long long *slot = pcg_slot(P, q, buf, P.rank);
-            for (int e = threadIdx.x; e < K; e += blockDim.x) {
-                if (e < 4) {
-                    if (q != P.rank) pcg_ll_store(slot, e, s_loc[e], seq);
-                } else {
-                    const int gi = (e - 4) / per, second = (e - 4) - gi * per;
-                    const int j = 4 + second * n + __ldcg(a.gl_list + gi);
-                    pcg_ll_store(slot, j, __ldcg(a.payload + j), seq);
+        if (P.world > 1) {
+            // the scalars to the other ranks; the straddling clusters' entries to every rank, this one included
+            const int ng = (int)__ldcg(&a.sync->n_global);
+            const int per = with_b ? 2 : 1, K = 4 + per * ng;
+            for (int q = 0; q < P.world; ++q) {
+                unsigned long long *slot = pcg_slot(P, q, buf, P.rank);
+                for (int e = threadIdx.x; e < K; e += blockDim.x) {
+                    if (e < 4) {
+                        if (q != P.rank) pcg_ll_store(slot, e, s_loc[e], seq);
+                    } else {
+                        const int gi = (e - 4) / per, second = (e - 4) - gi * per;
+                        const int j = 4 + second * n + __ldcg(a.gl_list + gi);
+                        pcg_ll_store(slot, j, __ldcg(a.payload + j), seq);
+                    }
                 }
             }
+            // the other ranks' scalars: thread (e, q) waits for entry e of rank q; sums in rank order
+            double *s_w = sh;   // [8][4] staged values of eight ranks at a time
+            for (int q0 = 0; q0 < P.world; q0 += 8) {
+                const int e = (int)threadIdx.x & 3, q = q0 + ((int)threadIdx.x >> 2);
+                __syncthreads();
+                if (threadIdx.x < 32 && q < P.world) {
+                    int err = 0;
+                    s_w[threadIdx.x] = q == P.rank ? s_loc[e] : pcg_ll_load(P, buf, q, e, seq, &err);
+                    if (err) { s_err = err; a.sc->pad = err; }
+                }
+                __syncthreads();
+                if (threadIdx.x < 4) {
+                    double acc2 = q0 == 0 ? 0.0 : out[threadIdx.x];
+                    for (int u = 0; u < 8 && q0 + u < P.world; ++u) acc2 += s_w[4 * u + threadIdx.x];
+                    out[threadIdx.x] = acc2;
+                }
+            }
+            __syncthreads();
+        } else {
+            if (threadIdx.x < 4) out[threadIdx.x] = s_loc[threadIdx.x];
+            __syncthreads();
         }
+        if (threadIdx.x < 4) a.sync->sums[buf][threadIdx.x] = out[threadIdx.x];
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            unsigned long long *mine = pcg_slot(P, P.rank, buf, P.rank);
-            for (int j = 0; j < 4; ++j) pcg_ll_store(mine, j, s_loc[j], seq);
+            st_release_gpu(&a.sync->gen_r, rseq);
         }
-    }
-    // one thread per (entry, rank): all polls in flight together; sums in rank order
-    double *s_w = sh;   // [world][4] staged words (world <= 8 here; larger worlds loop)
-    for (int q0 = 0; q0 < P.world; q0 += 8) {
-        const int e = (int)threadIdx.x & 3, q = q0 + ((int)threadIdx.x >> 2);
-        if (threadIdx.x < 32 && q < P.world) {
-            int err = 0;
-            s_w[threadIdx.x] = pcg_ll_load(P, buf, q, e, seq, &err);
-            __threadfence();   // acquire side of the local barrier (fence - relaxed store / relaxed load - fence)
-            if (err) { s_err = err; a.sc->pad = err; }
+    } else {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (ld_relaxed_gpu(&a.sync->gen_r) < rseq)
+                if (clock64() - t0 > kP2pTimeoutCycles) { s_err = 2; a.sc->pad = 2; break; }
+            (void)ld_acquire_gpu(&a.sync->gen_r);
         }
         __syncthreads();
-        if (threadIdx.x < 4) {
-            double acc = q0 == 0 ? 0.0 : out[threadIdx.x];
-            for (int u = 0; u < 8 && q0 + u < P.world; ++u) acc += s_w[4 * u + threadIdx.x];
-            out[threadIdx.x] = acc;
-        }
-        __syncthreads();
+        if (threadIdx.x < 4) out[threadIdx.x] = __ldcg(&a.sync->sums[buf][threadIdx.x]);
     }
+    __syncthreads();
     return s_err != 0;
 }
 
@@ -283,9 +318,10 @@ __device__ __forceinline__ double pcg_warp_row_dot(const PcgArgs &a, const doubl
 // in flight needed 64 registers, ran 4 CTAs per SM instead of 6 and was slower), so the phase is written to
 // live in the 40 registers that keep six CTAs resident.
 template <int MODE>
-__device__ __forceinline__ double pcg_spmv_tiles(const PcgArgs &a, const double *g, double *y, double *prod) {
+__device__ __forceinline__ double pcg_spmv_tiles(const PcgArgs &a, const double *g, double *y, double *prod, int t_first,
+                                                 int t_end, int t_step) {
     double local = 0.0;
-    for (int t = a.t0 + (int)blockIdx.x; t < a.t1; t += (int)gridDim.x) {
+    for (int t = t_first; t < t_end; t += t_step) {
         const int4 ti = __ldg(a.tile_info + t);
         const int r0 = ti.x, r1 = ti.y;
         if (r0 < r1) {
@@ -384,8 +420,8 @@ __device__ __forceinline__ void pcg_cluster_rows(const PcgArgs &a, const double 
 // The scalars of the recurrence live in SHARED memory between the phases (every CTA keeps its own identical
 // copy), not in registers: a phase then needs no more registers than the same code as a kernel of its own.
 struct PcgState {
-    double alpha, beta, gamma, stop, bb;
-    int done, err;
+    double alpha, beta, gamma, stop, bb, gmin;
+    int done, err, it_min;
 };
 
 template <int MINB, bool PROF>
@@ -435,7 +471,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
         pcg_barrier_halo(a, a.hseq0 + 1, pushed);
     }
     // ---- init 1: r = b - A x; cluster sums of r and of b
-    pcg_spmv_tiles<2>(a, g, a.r, prod);
+    pcg_spmv_tiles<2>(a, g, a.r, prod, a.t0 + cta, a.t1, G);
     if (clustered) pcg_cluster_rows<2>(a, g);
     pcg_barrier_reduce(a, a.rseq0 + 1, 0, true, s_out, red);
     // ---- init 2: u = M^-1 r (into the window), gamma and b.M^-1 b partials, recurrence state
@@ -470,7 +506,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
     }
     // ---- init 3: w = A u; delta partial; cluster sums of w
     {
-        double ld = pcg_spmv_tiles<1>(a, g, a.w, prod);
+        double ld = pcg_spmv_tiles<1>(a, g, a.w, prod, a.t0 + cta, a.t1, G);
         if (clustered) pcg_cluster_rows<1>(a, g);
         ld = block_sum(ld, red);
         if (tid == 0) a.partials[(size_t)G + cta] = ld;
@@ -538,7 +574,7 @@ __global__ void __launch_bounds__(kSpmvThreads, MINB) pcg_persistent_kernel(cons
         // ---- S: w = A u; delta partial; cluster sums of w; the one reduction of the iteration
         {
             if (PROF && cta_prof) cp_t = pcg_now();
-            double ld = pcg_spmv_tiles<1>(a, g, a.w, prod);
+            double ld = pcg_spmv_tiles<1>(a, g, a.w, prod, a.t0 + cta, a.t1, G);
             PCG_PROF(3);
             if (clustered) pcg_cluster_rows<1>(a, g);
             ld = block_sum(ld, red);

@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <utility>
 #include <vector>
@@ -812,6 +813,19 @@ static int true_residual(dkmc_ctx *ctx, int m, const int *d_row_ptr, const int *
     return DKMC_OK;
 }
 
+// Tolerance of a restart's correction solve: a restart only has to bring the per-entry error estimate from
+// `est` below est_tol, so it is solved to est_tol / (kRestartMargin * est) relative to its own right-hand side,
+// never tighter than refine_tol and never looser than 1e-2 (DKMC_RESTART_MARGIN=0: always refine_tol, the round-1
+// behaviour).  If one restart falls short the next one finishes the job (refine_rounds).
+static double restart_tolerance(const dkmc_solver_opts &o, double est) {
+    static const double margin = [] { const char *e = getenv("DKMC_RESTART_MARGIN"); return e ? atof(e) : 30.0; }();
+    if (!(margin > 0.0) || !(est > 0.0)) return o.refine_tol;
+    double t = o.est_tol / (margin * est);
+    if (t < o.refine_tol) t = o.refine_tol;
+    if (t > 1e-2) t = 1e-2;
+    return t;
+}
+
 static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col,
                          const double *d_val, const double *d_rhs, double *d_x, CgWork &w,
                          const dkmc_solver_opts &o, dkmc_solve_info *info) {
@@ -826,10 +840,14 @@ static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, co
     // relative to ITS OWN right-hand side, i.e. on the scale of what is still wrong) until the
     // per-entry error estimate is at rounding level or the rounds are used up.
     int rounds = 0;
+    static const bool trace = getenv("DKMC_SOLVE_TRACE") != nullptr;
     if ((rc = true_residual(ctx, m, d_row_ptr, d_col, d_val, d_rhs, d_x, w, bb0, &rel, &est))) return rc;
+    if (trace) fprintf(stderr, "dkmc solve: first %d its -> rel %.2e est %.2e\n", iters, rel, est);
     while (rounds < o.refine_rounds && est > o.est_tol) {
         DKMC_LAUNCH(ctx, fill_kernel, vg, kVecThreads, 0, m, 0.0, w.e);
-        if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, w.res, w.e, w, o.refine_tol, o.max_iter, o.check_every, &iters, &conv, nullptr))) return rc;
+        const double rtol = restart_tolerance(o, est);
+        if ((rc = run_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, w.res, w.e, w, rtol, o.max_iter, o.check_every, &iters, &conv, nullptr))) return rc;
+        if (trace) fprintf(stderr, "dkmc solve: restart tol %.1e: %d its\n", rtol, iters);
         total += iters;
         DKMC_LAUNCH(ctx, axpy_kernel, vg, kVecThreads, 0, m, 1.0, w.e, d_x);
         ++rounds;
@@ -841,7 +859,7 @@ static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, co
         info->rel_residual = rel;
         info->est_error = est;
     }
-    return all_conv ? DKMC_OK : DKMC_ERR_NOT_CONVERGED;
+    return (all_conv || est <= o.est_tol) ? DKMC_OK : DKMC_ERR_NOT_CONVERGED;
 }
 
 // ================================================================ distributed PCG (x-slab rows per rank)
@@ -868,17 +886,19 @@ struct P2pPeers {
     unsigned char *base[DKMC_MAX_RANKS];
     int world, rank;
     size_t red_off, red2_off, flag_off;   // reduction slots of the per-op kernels / of the persistent PCG, flags
+    size_t vec2_off;                      // second gather vector (pipelined PCG)
 };
 
-// window = [ vector (m doubles) | slots [2][world][kP2pRedCap] | the same again | flags [8][DKMC_MAX_RANKS] ]
+// window = [ vector (m doubles) | second vector | slots [2][world][kP2pRedCap] | the same again | flags [8][DKMC_MAX_RANKS] ]
 static size_t window_layout(int m, int world, P2pPeers *P) {
     const size_t pbytes = (((size_t)m + 64) * sizeof(double) + 255) & ~(size_t)255;
     const size_t rbytes = (size_t)2 * world * kP2pRedCap * sizeof(double);
     const size_t fbytes = (size_t)8 * DKMC_MAX_RANKS * sizeof(unsigned long long);
-    P->red_off = pbytes;
-    P->red2_off = pbytes + rbytes;
-    P->flag_off = pbytes + 2 * rbytes;
-    return pbytes + 2 * rbytes + fbytes;
+    P->vec2_off = pbytes;
+    P->red_off = 2 * pbytes;
+    P->red2_off = 2 * pbytes + rbytes;
+    P->flag_off = 2 * pbytes + 2 * rbytes;
+    return 2 * pbytes + 2 * rbytes + fbytes;
 }
 
 struct DistState {
@@ -937,6 +957,7 @@ struct P2pHalo {
 };
 
 #include "pcg_persistent.cuh"
+#include "pcg_pipelined.cuh"
 
 static bool use_persistent_pcg(const dkmc_ctx *ctx) { return !ctx->legacy_cg; }
 constexpr int kPcgProfLen = 8 + 2 * 2048;   // phase sums of CTA 0 | per CTA: SpMV-phase time, wait at barrier R
@@ -946,16 +967,22 @@ constexpr int kPcgProfLen = 8 + 2 * 2048;   // phase sums of CTA 0 | per CTA: Sp
 // Three instantiations trade registers per thread (loads in flight) against CTAs per SM: *variant = 0, 1, 2 for
 // launch bounds of 6, 5, 4 CTAs per SM (40, 48, 64 registers).
 typedef void (*PcgKernel)(const PcgArgs);
-static const PcgKernel kPcgKernels[3] = {pcg_persistent_kernel<6, false>, pcg_persistent_kernel<5, false>, pcg_persistent_kernel<4, false>};
-static const PcgKernel kPcgKernelsProf[3] = {pcg_persistent_kernel<6, true>, pcg_persistent_kernel<5, true>, pcg_persistent_kernel<4, true>};
+// family 0: Chronopoulos-Gear (two synchronisations per iteration), family 1: pipelined (one)
+static const PcgKernel kPcgKernels[2][3] = {
+    {pcg_persistent_kernel<6, false>, pcg_persistent_kernel<5, false>, pcg_persistent_kernel<4, false>},
+    {pcg_pipelined_kernel<6, false>, pcg_pipelined_kernel<5, false>, pcg_pipelined_kernel<4, false>}};
+static const PcgKernel kPcgKernelsProf[2][3] = {
+    {pcg_persistent_kernel<6, true>, pcg_persistent_kernel<5, true>, pcg_persistent_kernel<4, true>},
+    {pcg_pipelined_kernel<6, true>, pcg_pipelined_kernel<5, true>, pcg_pipelined_kernel<4, true>}};
 
-static int pcg_ctas_per_sm(dkmc_ctx *ctx, int *variant) {
-    static int occ[3] = {0, 0, 0}, regs[3] = {0, 0, 0};
+static int pcg_ctas_per_sm(dkmc_ctx *ctx, int family, int *variant) {
+    static int occ_all[2][3] = {{0, 0, 0}, {0, 0, 0}}, regs_all[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    int *occ = occ_all[family], *regs = regs_all[family];
     if (!occ[0]) {
         for (int v = 0; v < 3; ++v) {
             cudaFuncAttributes fa;
-            regs[v] = cudaFuncGetAttributes(&fa, kPcgKernels[v]) == cudaSuccess ? fa.numRegs : 40 + 8 * v;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], kPcgKernels[v], kSpmvThreads, 0) != cudaSuccess || occ[v] < 1) occ[v] = 1;
+            regs[v] = cudaFuncGetAttributes(&fa, kPcgKernels[family][v]) == cudaSuccess ? fa.numRegs : 40 + 8 * v;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], kPcgKernels[family][v], kSpmvThreads, 0) != cudaSuccess || occ[v] < 1) occ[v] = 1;
         }
     }
     // DKMC_PCG_CPS="alone_cps,alone_variant,overlap_cps,overlap_variant" overrides (0 / -1: default)
@@ -991,9 +1018,43 @@ struct PcgGeometry {
     unsigned long long *pseq_r, *pseq_h;
 };
 
+static int run_pcg_persistent_family(dkmc_ctx *ctx, int family, int m, const int *d_row_ptr, const int *d_col, const double *d_val,
+                                     const double *d_b, double *d_x, const CgWork &w, const PcgGeometry &geo, double tol,
+                                     int max_iter, int *iters_out, int *converged, double *bb_out, int *fallback);
+
+// The persistent-kernel PCG: the pipelined kernel (one synchronisation per iteration) unless it is switched off
+// (dkmc_ctx_set_pcg_pipelined / DKMC_PCG_PIPELINED=0) or some CTA's rows touch more clusters than its shared-memory
+// table holds — then, on every rank alike, the Chronopoulos-Gear kernel.
 static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const int *d_col, const double *d_val,
                               const double *d_b, double *d_x, const CgWork &w, const PcgGeometry &geo, double tol,
                               int max_iter, int *iters_out, int *converged, double *bb_out) {
+    // auto (-1): on several GPUs only — on one GPU there is no NVLink round trip to hide and the extra vector costs
+    // more than the second barrier (measured at 1 M sites: 150 vs 145 us per iteration beside the pairwise sum).
+    // Never without the cluster coarse space: the pipelined recurrences stagnate on the undeflated matrix.
+    // Only for the restarts' correction solves (tolerance 1e-6 .. 1e-2 relative to their own right-hand side, far
+    // above the floor of the pipelined recurrences): the first solve of a step runs to 1e-12, where the pipelined
+    // recurrence residual stagnates in about one step out of six (measured, 1 M sites) — and the restarts are two
+    // thirds of a step's iterations.
+    const bool want = (ctx->pcg_pipelined < 0 ? geo.peers.world > 1 : ctx->pcg_pipelined != 0) && tol >= 1e-8;
+    int done_its = 0;
+    if (want && w.P.pos != nullptr) {
+        int fallback = 0;
+        int rc = run_pcg_persistent_family(ctx, 1, m, d_row_ptr, d_col, d_val, d_b, d_x, w, geo, tol, max_iter, iters_out, converged,
+                                           bb_out, &fallback);
+        if (rc != DKMC_OK) return rc;
+        if (!fallback && *converged) return rc;
+        // table overflow, stagnation or max_iter: the other recurrence carries on from the current x
+        if (!fallback) done_its = *iters_out;
+    }
+    int rc = run_pcg_persistent_family(ctx, 0, m, d_row_ptr, d_col, d_val, d_b, d_x, w, geo, tol, max_iter, iters_out, converged, bb_out,
+                                       nullptr);
+    *iters_out += done_its;
+    return rc;
+}
+
+static int run_pcg_persistent_family(dkmc_ctx *ctx, int family, int m, const int *d_row_ptr, const int *d_col, const double *d_val,
+                                     const double *d_b, double *d_x, const CgWork &w, const PcgGeometry &geo, double tol,
+                                     int max_iter, int *iters_out, int *converged, double *bb_out, int *fallback) {
     PcgArgs a;
     memset(&a, 0, sizeof(a));
     int rc;
@@ -1006,8 +1067,10 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
     if ((rc = ensure<double>(ctx, S_DIST_RED, (size_t)4 + 2 * (size_t)n + 8, &payload))) return rc;
     int *clk;
     if ((rc = ensure<int>(ctx, S_PCG_CLK, (size_t)2 * n + 8, &clk))) return rc;
-    const bool fresh = ctx->slot_ptr[S_PCG_SYNC] == nullptr;
-    if ((rc = ensure<PcgSync>(ctx, S_PCG_SYNC, 1, &sync))) return rc;
+    // one per sequence owner (the single-GPU window and the distributed one count separately)
+    const int sync_slot = geo.peers.world > 1 ? S_PCG_SYNC2 : S_PCG_SYNC;
+    const bool fresh = ctx->slot_ptr[sync_slot] == nullptr;
+    if ((rc = ensure<PcgSync>(ctx, sync_slot, 1, &sync))) return rc;
     if (fresh) DKMC_CUDA(cudaMemsetAsync(sync, 0, sizeof(PcgSync), ctx->stream));
     DKMC_CUDA(cudaMemsetAsync(&sync->n_global, 0, sizeof(unsigned int), ctx->stream));
     static const bool want_prof = getenv("DKMC_PCG_PROF") != nullptr;
@@ -1020,6 +1083,11 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
     a.m = m; a.ra = geo.ra; a.rb = geo.rb; a.t0 = geo.t0; a.t1 = geo.t1; a.n_cl = n; a.max_iter = max_iter;
     a.row_ptr = d_row_ptr; a.col = d_col; a.val = d_val; a.dinv = w.dinv; a.b = d_b; a.tile_info = w.tile_row;
     a.x = d_x; a.r = w.r[0]; a.w = w.Ap; a.p = w.p; a.s = s_vec;
+    if (family == 1) {
+        if ((rc = ensure<double>(ctx, S_CG_PZ, (size_t)m, &a.z))) return rc;
+        if ((rc = ensure<double>(ctx, S_CG_PN, (size_t)m, &a.nvec))) return rc;
+        a.g2_off = geo.peers.vec2_off;
+    }
     a.P = w.P;
     a.cs = rec; a.cr = rec + 2 * (size_t)n;
     a.cl_kind = clk; a.gl_list = clk + n + 4;
@@ -1029,15 +1097,19 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
     a.peers = geo.peers; a.halo = geo.halo; a.prof = prof;
     const int rows = geo.rb - geo.ra, nt = geo.t1 - geo.t0;
     int variant = 0;
-    int grid = ctx->num_sms * pcg_ctas_per_sm(ctx, &variant);
+    int grid = ctx->num_sms * pcg_ctas_per_sm(ctx, family, &variant);
     int need = ceil_div(rows > 0 ? rows : 1, kSpmvThreads);
     if (nt > need) need = nt;
     if (grid > need) grid = need;
     if ((size_t)3 * grid > (size_t)ctx->num_sms * 32) grid = ctx->num_sms * 32 / 3;   // partials capacity (cg_workspace)
     if (grid > 2048) grid = 2048;
     DKMC_CUDA(cudaMemsetAsync(&w.sc->pad, 0, sizeof(int), ctx->stream));
+    static const bool trace = getenv("DKMC_SOLVE_TRACE") != nullptr;
+    static cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+    if (trace && !tev0) { cudaEventCreate(&tev0); cudaEventCreate(&tev1); }
+    if (trace) cudaEventRecord(tev0, ctx->stream);
     {
-        const PcgKernel kern = (prof ? kPcgKernelsProf : kPcgKernels)[variant];
+        const PcgKernel kern = (prof ? kPcgKernelsProf : kPcgKernels)[family][variant];
         DKMC_SET_CARVEOUT_FN(kern);
         kern<<<grid, kSpmvThreads, 0, ctx->stream>>>(a);
         ctx->launches++;
@@ -1047,9 +1119,22 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
             return DKMC_ERR_CUDA;
         }
     }
+    if (trace) cudaEventRecord(tev1, ctx->stream);
     CgScalars h;
     DKMC_CUDA(cudaMemcpyAsync(&h, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
     DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (trace) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tev0, tev1);
+        fprintf(stderr, "dkmc pcg launch: rank %d family %d grid %d (variant %d) rows %d tiles %d n_cl %d: %d its, %.3f ms, pad %d\n",
+                geo.peers.rank, family, grid, variant, rows, nt, n, h.iters, ms, h.pad);
+    }
+    if (h.pad == 5 && family == 1 && fallback) {   // table overflow on some rank: every rank left after the first barrier
+        *geo.pseq_r = h.rseq_end;
+        *geo.pseq_h = h.hseq_end;
+        *fallback = 1;
+        return DKMC_OK;
+    }
     if (h.pad != 0) {
         set_error("persistent PCG: a wait timed out (code %d: 2 local barrier, 3 neighbour halo, 4 reduction) — a CTA could "
                   "not become resident or a peer GPU did not answer", h.pad);
@@ -1074,9 +1159,8 @@ static int self_window(dkmc_ctx *ctx, int m, SelfWindow **out) {
         DKMC_CUDA(cudaMemsetAsync(sw->base, 0, bytes, ctx->stream));
         sw->m_cap = m + m / 8;
         sw->peers.world = 1; sw->peers.rank = 0; sw->peers.base[0] = sw->base;
-        // a new window starts with zeroed flags: restart the sequences — but the local barrier's generation
-        // counter (PcgSync) is monotonic, so keep counting the halo sequence and only rewind the reductions' flags
-        sw->pseq_r = 0;
+        // a new window starts with zeroed flags and slots, but the local barriers' generation counters (PcgSync)
+        // are monotonic: keep counting both sequences (the LL words of a reduction are matched by equality)
     }
     *out = sw;
     return DKMC_OK;
@@ -1532,17 +1616,20 @@ static int dist_solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_pt
     if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, d, o.rel_tol, o.max_iter, o.check_every, &iters, &conv))) return rc;
     total += iters;
     bool all_conv = conv != 0;
+    static const bool trace = getenv("DKMC_SOLVE_TRACE") != nullptr;
     if ((rc = dist_true_residual(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, d, &est))) return rc;
+    if (trace && dist_of(ctx)->rank == 0) fprintf(stderr, "dkmc dist solve: first %d its conv %d -> est %.2e\n", iters, conv, est);
     while (rounds < o.refine_rounds && est > o.est_tol) {
         DKMC_CUDA(cudaMemsetAsync(d.w.e, 0, (size_t)m * sizeof(double), ctx->stream));
-        if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d.w.res, d.w.e, d, o.refine_tol, o.max_iter, o.check_every, &iters, &conv))) return rc;
+        if ((rc = dist_pcg(ctx, m, nnz, d_row_ptr, d_col, d_val, d.w.res, d.w.e, d, restart_tolerance(o, est), o.max_iter, o.check_every, &iters, &conv))) return rc;
+        if (trace && dist_of(ctx)->rank == 0) fprintf(stderr, "dkmc dist solve: restart: %d its conv %d\n", iters, conv);
         total += iters;
         if (rows > 0) DKMC_LAUNCH(ctx, axpy_range_kernel, vg, kVecThreads, 0, d.ra, d.rb, 1.0, d.w.e, d_x);
         ++rounds;
         if ((rc = dist_true_residual(ctx, m, nnz, d_row_ptr, d_col, d_val, d_rhs, d_x, d, &est))) return rc;
     }
     if (info) { info->iterations = total; info->refinements = rounds; info->rel_residual = 0.0; info->est_error = est; }
-    return all_conv ? DKMC_OK : DKMC_ERR_NOT_CONVERGED;
+    return (all_conv || est <= o.est_tol) ? DKMC_OK : DKMC_ERR_NOT_CONVERGED;
 }
 
 }  // namespace dkmc
@@ -1730,6 +1817,12 @@ int dkmc_ctx_set_legacy_cg(dkmc_ctx *ctx, int on) {
     return DKMC_OK;
 }
 
+int dkmc_ctx_set_pcg_pipelined(dkmc_ctx *ctx, int on) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    ctx->pcg_pipelined = on ? 1 : 0;
+    return DKMC_OK;
+}
+
 int dkmc_pcg_profile(dkmc_ctx *ctx, double *out8) {
     DKMC_REQUIRE(ctx && out8, "null pointer");
     for (int q = 0; q < 8; ++q) out8[q] = 0.0;
@@ -1753,6 +1846,7 @@ int dkmc_pcg_profile(dkmc_ctx *ctx, double *out8) {
         std::sort(sv.begin(), sv.end());
         const double it = (double)h[6] * 1e3;
         const size_t n = sv.size();
+        if (n == 0) return DKMC_OK;   // the pipelined kernel keeps no per-CTA times
         fprintf(stderr, "dkmc pcg prof: %zu CTAs; SpMV phase us/it min %.1f p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f; wait at barrier R min %.1f max %.1f; slowest (cta@sm):",
                 n, sv[0].first / it, sv[n / 10].first / it, sv[n / 2].first / it, sv[n * 9 / 10].first / it, sv[n * 99 / 100].first / it,
                 sv[n - 1].first / it, wmin / it, wmax / it);
@@ -1873,6 +1967,8 @@ int dkmc_dist_finalize(dkmc_ctx *ctx) {
             for (int r = 0; r < ds->world; ++r)
                 if (r != ds->rank && ds->peers.base[r]) cudaIpcCloseMemHandle(ds->peers.base[r]);
         if (ds->win) cudaFree(ds->win);
+        // the distributed PCG's barrier generations restart with the next DistState's sequences
+        if (ctx->slot_ptr[S_PCG_SYNC2]) cudaMemset(ctx->slot_ptr[S_PCG_SYNC2], 0, sizeof(PcgSync));
         if (ds->comm) ncclCommDestroy(ds->comm);
         delete ds;
         ctx->dist = nullptr;

@@ -132,7 +132,9 @@ class SlabSim:
         self.sp = self.buf.sparsity(self.nc, self.nc)
         # the pairwise kernel's share of each SM while it runs beside the CG: the fewer targets a rank
         # owns, the smaller the share it needs to finish before the CG does
-        share = (3, 128) if world == 1 else ((2, 128) if world == 2 else (1, 128))
+        # (measured at 1 M sites, round 2: with two CTAs of 128 threads per SM the sum ends before the CG at every
+        # N >= 2 and the CG is no slower than beside one CTA — its iterations are latency-bound there)
+        share = (3, 128) if world == 1 else (2, 128)
         if os.environ.get("DKMC_PW_SHARE"):     # experiments: "blocks_per_sm,threads"
             share = tuple(int(v) for v in os.environ["DKMC_PW_SHARE"].split(","))
         from ._capi import check
@@ -161,6 +163,9 @@ class SlabSim:
                    self.i0, self.i1, self._pc_full.data_ptr())
         if self.i1 > self.i0:
             check(lib.dkmc_poisson_gridless_begin(*pw_args))
+        pw_ms = C.c_double(0.0)
+        if os.environ.get("DKMC_PW_SERIAL"):    # experiment: the pairwise sum BEFORE the CG instead of beside it
+            check(lib.dkmc_poisson_gridless_join(dev.ctx.h, C.byref(pw_ms)))
         if self.dcg is not None:
             st = self.dcg.solve(Vd, info)
         else:
@@ -170,8 +175,8 @@ class SlabSim:
                 buf.metal_types.data_ptr(), buf.num_metal_types_, buf.site_potential_boundary.data_ptr(), None,
                 C.byref(info))
             check(st, allow=(3,))
-        pw_ms = C.c_double(0.0)
-        check(lib.dkmc_poisson_gridless_join(dev.ctx.h, C.byref(pw_ms)))
+        if not os.environ.get("DKMC_PW_SERIAL"):
+            check(lib.dkmc_poisson_gridless_join(dev.ctx.h, C.byref(pw_ms)))
         if self.world > 1:
             if self.dcg is not None and self.dcg.p2p:
                 # every rank pulls the other ranks' target rows from their peer windows (no NCCL call)
@@ -247,6 +252,9 @@ def bench_multi_gpu(args, metric: str, unit: str):
                                      "cluster_rows": buf8[4] / it / 1e3, "barrier_reduce": buf8[5] / it / 1e3},
                 "setup_us_per_solve": buf8[0] / max(buf8[7], 1.0) / 1e3, "iterations": buf8[6], "solves": buf8[7],
                 "note": "profiling kernels carry extra registers: the timings of such a run are not bench values"}
+        allp = [None] * world
+        dist.all_gather_object(allp, prof["us_per_iteration"])
+        prof["per_rank"] = {k: [round(q[k], 1) for q in allp] for k in allp[0]}
     # e2e: host buffers in and out every step, on every rank
     ckpt.restore(s.buf, s.sim, s.dev)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()

@@ -14,6 +14,7 @@ for path in sys.argv[1:]:
         if d.get("pcg_profile"):
             out["pcg_us_it"] = {k: round(v, 1) for k, v in d["pcg_profile"]["us_per_iteration"].items()}
             out["pcg_setup_us"] = round(d["pcg_profile"]["setup_us_per_solve"], 0)
+            out["pcg_per_rank"] = d["pcg_profile"].get("per_rank")
         if d.get("per_step"):
             out["events"] = d["per_step"].get("events")
         print(path, json.dumps(out))
