@@ -30,10 +30,24 @@ UNIT = "steps/s"
 def workload(name):
     from devicekmc_b200 import structures as S
     from devicekmc_b200.host import KMCParameters
-    ny, nz = S.WORKLOADS[name]
-    el, x, y, z, lat, nc = S.tile_device(ny, nz)
+    if name in S.REAL_WORKLOADS:      # a shipped structure, sites in the reference's order
+        data, ny, nz = S.REAL_WORKLOADS[name]
+        el, x, y, z, lat, nc, _vd = S.tile_structure(data, ny, nz)
+    else:
+        ny, nz = S.WORKLOADS[name]
+        el, x, y, z, lat, nc = S.tile_device(ny, nz)
     p = KMCParameters(lattice=tuple(lat), num_atoms_contact=nc, num_atoms_first_layer=nc)
     return el, x, y, z, lat, nc, p
+
+
+def workload_vd(name, vd):
+    """the bias of a workload: --vd, else the V_switch of the structure's parameters.txt (10 V for the synthetic tiles)"""
+    from devicekmc_b200 import structures as S
+    if vd is not None:
+        return float(vd)
+    if name in S.REAL_WORKLOADS:
+        return S.load_structure(S.REAL_WORKLOADS[name][0])[6]
+    return 10.0
 
 
 def substoichiometric(el, p):
@@ -246,6 +260,9 @@ def gpu_arm(args):
         ep0.record()
         o = dev.updatePotential(buf, p, Vd, n_contact=nc)
         ep1.record()
+        if not o["cg_converged"]:
+            raise RuntimeError(f"the CG of the boundary potential did not converge ({o['cg_iterations']} iterations, "
+                               f"error estimate {o['cg_est_error']:.1e}): not a benchmark step")
         sim.executeKMCStep(buf, dev)
         if e2e:
             buf.sync_GPUToHost(dev)
@@ -333,6 +350,19 @@ def gpu_arm(args):
     spmv_ms = e0.elapsed_time(e1) / reps
     spmv_bytes = 12.0 * nnz + 20.0 * m
     spmv_gbs = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    # the same product on the structure the SOLVER works on: for inputs in the reference's site order that is the
+    # matrix in the registered internal row order (dkmc_solver_set_order), otherwise the same CSR again
+    spmv_int_ms = spmv_ms
+    if buf.solver_order_applied:
+        rp2, col2 = C.c_void_p(), C.c_void_p()
+        check(lib.dkmc_solver_csr(dev.ctx.h, C.byref(sp), C.byref(rp2), C.byref(col2), None))
+        for _ in range(5):
+            check(lib.dkmc_spmv(dev.ctx.h, m, nnz, rp2, col2, val.data_ptr(), xv.data_ptr(), yv.data_ptr()))
+        e0.record()
+        for _ in range(reps):
+            check(lib.dkmc_spmv(dev.ctx.h, m, nnz, rp2, col2, val.data_ptr(), xv.data_ptr(), yv.data_ptr()))
+        e1.record(); e1.synchronize()
+        spmv_int_ms = e0.elapsed_time(e1) / reps
     fp64 = C.c_double(0)
     check(lib.dkmc_probe_fp64_tflops(dev.ctx.h, C.byref(fp64)))
     ncharged = int((buf.site_charge != 0).sum().item())
@@ -377,7 +407,13 @@ def gpu_arm(args):
         pipe_pct = tj.get("pairwise_fp64_pipe_pct")
     rooflines = {
         "spmv": {"bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
-                 "traffic": None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "peak_source": peak_src},
+                 "traffic": None, "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms, "peak_source": peak_src,
+                 "order": "caller's site order" + (" (the reference's: lattice atoms before interstitials)" if buf.solver_order_applied else " (x-major grid cells)")},
+        "spmv_solver_order": {"bound": "hbm", "achieved": spmv_bytes / (spmv_int_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": spmv_bytes / (spmv_int_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                              "bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_int_ms,
+                              "order": "internal row order of the solver (x-major grid cells)" if buf.solver_order_applied
+                                       else "same structure as `spmv`"},
         "pairwise": {"bound": "fp64", "achieved": pair_tflops, "peak": fp64.value, "unit": "TFLOP/s",
                      "frac": pair_tflops / fp64.value if fp64.value else None, "traffic": None,
                      "flops_per_pair": 200, "pairs": pairs, "pairs_all": pairs_total,
@@ -396,7 +432,7 @@ def gpu_arm(args):
     rooflines["pairwise"]["note"] = ("achieved = 200 contract flop/pair / time; the kernel needs ~62 FP64 instructions "
                                      "per pair, so frac > 1 is work saved; pipe utilisation = fp64_pipe_active_pct_ncu")
     dominant = max((k_ for k_ in shares if k_ != "potential"), key=shares.get)
-    roof_key = {"pairwise": "pairwise", "cg_solve": "spmv", "assemble": "spmv", "rate_table": "rate_table",
+    roof_key = {"pairwise": "pairwise", "cg_solve": "spmv_solver_order", "assemble": "spmv_solver_order", "rate_table": "rate_table",
                 "event_loop": "rate_table"}[dominant]
     roofline = dict(rooflines[roof_key]); roofline["kernel"] = roof_key; roofline["dominant_stage"] = dominant
 
@@ -430,7 +466,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tiled_1M")
-    ap.add_argument("--vd", type=float, default=10.0)
+    ap.add_argument("--vd", type=float, default=None, help="bias [V]; default: the workload's own (10 V for the synthetic tiles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--events-per-step", type=int, default=350,
                     help="--impl reference: events per KMC step the bounded event-loop sample is scaled to (the mean of "
@@ -440,6 +476,7 @@ def main():
                          "slab-partitioned CG whose per-iteration exchange goes through NVLink peer memory")
     ap.add_argument("--distributed-cg", action="store_true", help=argparse.SUPPRESS)  # the default since round 1
     args = ap.parse_args()
+    args.vd = workload_vd(args.workload, args.vd)
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -54,8 +54,11 @@ class DistributedSolver:
         dist.broadcast_object_list(box, src=0)
         check(lib.dkmc_dist_init(sim.dev.ctx.h, sim.rank, sim.world, box[0]))
         sp = sim.sp
-        row_ptr = _device_ints(sp.d_row_ptr, sp.m + 1)
-        col = _device_ints(sp.d_col, sp.nnz)
+        # the CSR structure the solver works on: the caller's, or its image in the registered internal row order
+        rp_ptr, col_ptr = C.c_void_p(), C.c_void_p()
+        check(lib.dkmc_solver_csr(sim.dev.ctx.h, C.byref(sp), C.byref(rp_ptr), C.byref(col_ptr), None))
+        row_ptr = _device_ints(rp_ptr.value, sp.m + 1)
+        col = _device_ints(col_ptr.value, sp.nnz)
         self.plan = make_plan(row_ptr, col, sim.world, sim.rank, lib.dkmc_spmv_tile_nnz())
         self.p2p = False
         if p2p and os.environ.get("DKMC_P2P", "1") != "0":

@@ -16,7 +16,7 @@ namespace dkmc {
 
 constexpr int kWarp = 32;
 constexpr int kMaxLayers = 16;
-constexpr int kNumSlots = 64;
+constexpr int kNumSlots = 96;
 constexpr int kMaxLevels = 8;
 
 void set_error(const char *fmt, ...);
@@ -51,7 +51,7 @@ enum Slot : int {
     S_SP_CNT, S_SCAN_BLOCK,
     S_PW_FLAGS, S_PW_SRC, S_PW_COUNT,
     S_EV_TYPE, S_EV_PROB, S_EV_LEVELS, S_EV_STATE, S_EV_UNIFORMS, S_EV_EVENTS, S_EV_SCRATCH,
-    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_S, S_CL_REC, S_PCG_SYNC, S_PCG_SYNC2, S_PCG_PROF, S_PCG_CLK, S_CG_PZ, S_CG_PN, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
+    S_SCAN_TMP, S_SEL_OUT, S_CL_INT, S_CL_KEYS, S_CL_W, S_DIST_RED, S_PW_TILECTR, S_CG_S, S_CL_REC, S_PCG_SYNC, S_PCG_SYNC2, S_PCG_PROF, S_PCG_CLK, S_CG_PZ, S_CG_PN, S_ORD_VAL, S_ORD_VEC, S_ORD_CLS, S_ORD_TMP, S_PW_BOX, S_PW_CELLS, S_PW_SRC2, S_PW_IDX2,
     S_NB_HOSTPOS, S_NB_HOSTTAB, S_PW_PREVQ, S_PW_DQ, S_SNAP_STAGE, S_EV_NZROWS, S_EV_BATCHSUM,
     S_LAST
 };
@@ -98,6 +98,7 @@ struct dkmc_ctx {
     int exact_select = 0;
     void *dist = nullptr;  // DistState (NCCL communicator) when running slab-partitioned
     int legacy_cg = 0;     // 1: one kernel per CG operation (round-1 path) instead of the persistent PCG
+    void *solver_order = nullptr;   // SolverOrder (solver.cu): internal row order registered by dkmc_solver_set_order
     void *selfwin = nullptr;   // SelfWindow (solver.cu): the persistent PCG's window on one GPU
     int pw_regs_per_thread = 80;   // registers of the overlapped pairwise kernel (pairwise.cu refreshes it)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;

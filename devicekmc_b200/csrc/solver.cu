@@ -880,7 +880,8 @@ static int solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, co
 // after everybody finished reading the slots of n.  Latency: one NVLink store + flag round (~3 us)
 // instead of ~20-40 us per NCCL call, of which the PCG needs three per iteration.
 constexpr int kP2pRedCap = 1 << 15;               // doubles per rank and reduction
-constexpr long long kP2pTimeoutCycles = 4000000000ll;  // ~2 s: a lost peer becomes an error, not a hang
+constexpr long long kP2pTimeoutCycles = 40000000000ll;  // ~20 s: a lost peer becomes an error, not a hang (a peer that
+                                                         // is merely late — host work between two steps — must not)
 
 struct P2pPeers {
     unsigned char *base[DKMC_MAX_RANKS];
@@ -989,7 +990,9 @@ static int pcg_ctas_per_sm(dkmc_ctx *ctx, int family, int *variant) {
     static int cfg[4] = {0, -1, 0, -1};
     static bool cfg_read = false;
     if (!cfg_read) { const char *e = getenv("DKMC_PCG_CPS"); if (e) sscanf(e, "%d,%d,%d,%d", &cfg[0], &cfg[1], &cfg[2], &cfg[3]); cfg_read = true; }
-    const bool overlapped = ctx->pw_pending.active;
+    // beside the pairwise kernel only while that kernel is still running: a restart launched after the sum has
+    // finished (short sums: small devices, several GPUs) gets the whole GPU
+    const bool overlapped = ctx->pw_pending.active && cudaEventQuery(ctx->ev_pw1) == cudaErrorNotReady;
     int v = 0;
     const int cv = cfg[overlapped ? 3 : 1];
     if (cv >= 0 && cv < 3) v = cv;
@@ -1166,7 +1169,10 @@ static int self_window(dkmc_ctx *ctx, int m, SelfWindow **out) {
     return DKMC_OK;
 }
 
+static void free_order(dkmc_ctx *ctx);
+
 void free_solver_state(dkmc_ctx *ctx) {
+    free_order(ctx);
     SelfWindow *sw = static_cast<SelfWindow *>(ctx->selfwin);
     if (sw) {
         if (sw->base) cudaFree(sw->base);
@@ -1632,6 +1638,124 @@ static int dist_solve_refined(dkmc_ctx *ctx, int m, int nnz, const int *d_row_pt
     return (all_conv || est <= o.est_tol) ? DKMC_OK : DKMC_ERR_NOT_CONVERGED;
 }
 
+// ================================================================ internal row order of the solver
+// The public arrays keep the caller's site order (the reference puts all lattice atoms before all interstitials,
+// reorder_boundary.py:113-124: CSR bandwidth ~0.7 N, every SpMV gather a cache miss, and an index range is not a
+// slab).  dkmc_solver_set_order registers a permutation of the interior rows (e.g. x-major by grid cell); the
+// solver then works on P A P^T: the CSR structure is permuted once, every step the assembled values (computed in
+// the caller's order, so the diagonal keeps the reference's summation order bit for bit), the right-hand side,
+// 1/diag, the site classes and the starting vector are gathered into the internal order and the solution is
+// scattered back.  Nothing outside the solver sees the internal order.
+struct SolverOrder {
+    const int *key_row_ptr = nullptr;
+    int m = 0, nnz = 0;
+    int *order = nullptr, *inv = nullptr, *rp2 = nullptr, *col2 = nullptr, *map = nullptr;
+};
+
+__global__ void order_invert_kernel(int m, const int *__restrict__ order, int *__restrict__ inv, int *__restrict__ len2,
+                                    const int *__restrict__ rp, int *bad) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    const int r = order[p];
+    if (r < 0 || r >= m) { atomicAdd(bad, 1); return; }
+    if (atomicExch(inv + r, p) != -1) atomicAdd(bad, 1);   // not a permutation
+    len2[p] = rp[r + 1] - rp[r];
+}
+
+// row p of P A P^T: the entries of row order[p] with renumbered columns, ascending; map = where each came from
+__global__ void order_fill_kernel(int m, const int *__restrict__ order, const int *__restrict__ inv, const int *__restrict__ rp,
+                                  const int *__restrict__ col, const int *__restrict__ rp2, int *__restrict__ col2,
+                                  int *__restrict__ map) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    const int r = order[p], a = rp[r], n = rp[r + 1] - a, o = rp2[p];
+    for (int k = 0; k < n; ++k) {   // insertion sort into the output row (rows are a few dozen long)
+        const int c = inv[col[a + k]];
+        int j = k;
+        while (j > 0 && col2[o + j - 1] > c) { col2[o + j] = col2[o + j - 1]; map[o + j] = map[o + j - 1]; --j; }
+        col2[o + j] = c; map[o + j] = a + k;
+    }
+}
+
+__global__ void order_gather_vals_kernel(int nnz, const int *__restrict__ map, const double *__restrict__ val, double *__restrict__ val2) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += gridDim.x * blockDim.x) val2[k] = __ldcs(val + __ldg(map + k));
+}
+
+__global__ void order_gather_rows_kernel(int m, int NL, const int *__restrict__ order, const double *__restrict__ rhs,
+                                         const double *__restrict__ dinv, const unsigned char *__restrict__ cls,
+                                         const double *__restrict__ phi, double *__restrict__ rhs2, double *__restrict__ dinv2,
+                                         unsigned char *__restrict__ cls2, double *__restrict__ x2) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    const int r = order[p];
+    rhs2[p] = rhs[r]; dinv2[p] = dinv[r]; cls2[p] = cls[NL + r]; x2[p] = phi[NL + r];
+}
+
+__global__ void order_scatter_kernel(int m, int NL, const int *__restrict__ order, const double *__restrict__ x2, double *__restrict__ phi) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) phi[NL + order[p]] = x2[p];
+}
+
+static SolverOrder *order_of(dkmc_ctx *ctx, const dkmc_sparsity *sp) {
+    SolverOrder *so = static_cast<SolverOrder *>(ctx->solver_order);
+    return (so && so->key_row_ptr == sp->d_row_ptr && so->m == sp->m && so->nnz == sp->nnz) ? so : nullptr;
+}
+
+static void free_order(dkmc_ctx *ctx) {
+    SolverOrder *so = static_cast<SolverOrder *>(ctx->solver_order);
+    if (!so) return;
+    cudaFree(so->order); cudaFree(so->inv); cudaFree(so->rp2); cudaFree(so->col2); cudaFree(so->map);
+    delete so;
+    ctx->solver_order = nullptr;
+}
+
+// what the solver works on: the caller's CSR and arrays, or their internal-order images
+struct SolveView {
+    int m, nnz, NL;                 // NL: offset of interior row 0 in cls (0 in the internal order)
+    const int *rp, *col;
+    double *val, *rhs, *x;
+    const unsigned char *cls;
+    SolverOrder *so;
+    double *phi;                    // the caller's potential array (scatter target)
+    int phi_NL;
+};
+
+// val / rhs hold the matrix assembled in the caller's order (and S_CG_DINV / S_CLASS its 1/diag and classes)
+static int view_prepare(dkmc_ctx *ctx, const dkmc_sparsity *sp, int NL, double *val, double *rhs, double *phi, CgWork *w,
+                        SolveView *v) {
+    v->so = order_of(ctx, sp);
+    v->phi = phi; v->phi_NL = NL;
+    const unsigned char *cls = static_cast<const unsigned char *>(ctx->slot_ptr[S_CLASS]);
+    if (!v->so) {
+        v->m = sp->m; v->nnz = sp->nnz; v->NL = NL; v->rp = sp->d_row_ptr; v->col = sp->d_col;
+        v->val = val; v->rhs = rhs; v->x = phi + NL; v->cls = cls;
+        return DKMC_OK;
+    }
+    const int m = sp->m, nnz = sp->nnz;
+    double *val2, *rhs2, *dinv2, *x2;
+    unsigned char *cls2;
+    int rc;
+    if ((rc = ensure<double>(ctx, S_ORD_VAL, (size_t)nnz, &val2))) return rc;
+    if ((rc = ensure<double>(ctx, S_ORD_VEC, (size_t)3 * m, &rhs2))) return rc;
+    if ((rc = ensure<unsigned char>(ctx, S_ORD_CLS, (size_t)m, &cls2))) return rc;
+    dinv2 = rhs2 + m; x2 = rhs2 + 2 * (size_t)m;
+    int g = ceil_div(nnz, 256);
+    if (g > ctx->num_sms * 16) g = ctx->num_sms * 16;
+    DKMC_LAUNCH(ctx, order_gather_vals_kernel, g, 256, 0, nnz, v->so->map, val, val2);
+    DKMC_LAUNCH(ctx, order_gather_rows_kernel, ceil_div(m, 256), 256, 0, m, NL, v->so->order, rhs, w->dinv, cls, phi, rhs2, dinv2,
+                cls2, x2);
+    w->dinv = dinv2;
+    w->P.dinv = dinv2;
+    v->m = m; v->nnz = nnz; v->NL = 0; v->rp = v->so->rp2; v->col = v->so->col2;
+    v->val = val2; v->rhs = rhs2; v->x = x2; v->cls = cls2;
+    return DKMC_OK;
+}
+
+static int view_finish(dkmc_ctx *ctx, const SolveView &v) {
+    if (v.so) DKMC_LAUNCH(ctx, order_scatter_kernel, ceil_div(v.m, 256), 256, 0, v.m, v.phi_NL, v.so->order, v.x, v.phi);
+    return DKMC_OK;
+}
+
 }  // namespace dkmc
 
 using namespace dkmc;
@@ -1720,13 +1844,14 @@ int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int
     int rc;
     if ((rc = ensure<double>(ctx, S_CG_VAL, (size_t)sp->nnz, &val))) return rc;
     if ((rc = ensure<double>(ctx, S_CG_RHS, m, &rhs))) return rc;
-    if ((rc = cg_workspace(ctx, m, sp->nnz, sp->d_row_ptr, &w))) return rc;
+    if ((rc = cg_workspace(ctx, m, sp->nnz, order_of(ctx, sp) ? order_of(ctx, sp)->rp2 : sp->d_row_ptr, &w))) return rc;
     DKMC_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
     if ((rc = dkmc_assemble_K(ctx, sp, N, NL, NR, Vd, high_G, low_G, d_site_element, d_site_charge, d_metals,
                               num_metals, val, rhs))) return rc;
+    SolveView v;
+    if ((rc = view_prepare(ctx, sp, NL, val, rhs, d_site_potential_boundary, &w, &v))) return rc;
     if (o.cluster_precond) {
-        const unsigned char *cls = static_cast<const unsigned char *>(ctx->slot_ptr[S_CLASS]);
-        if ((rc = build_clusters(ctx, m, NL, cls, sp->d_row_ptr, sp->d_col, val, &w))) return rc;
+        if ((rc = build_clusters(ctx, m, v.NL, v.cls, v.rp, v.col, v.val, &w))) return rc;
     }
     DKMC_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
     if (g_flags & 4) {  // keep as much of the matrix as the persisting L2 carve-out holds
@@ -1748,9 +1873,9 @@ int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int
         if (!once) { once = true; fprintf(stderr, "dkmc: L2 persist %d MB, window %zu MB, hitRatio %.2f\n", max_persist >> 20, bytes >> 20, attr.accessPolicyWindow.hitRatio); }
     }
     // warm start: the interior of the previous potential (potential_solver_gpu.cu:754)
-    double *x = d_site_potential_boundary + NL;
-    rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info);
+    rc = solve_refined(ctx, m, sp->nnz, v.rp, v.col, v.val, v.rhs, v.x, w, o, info);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
+    { int rc2 = view_finish(ctx, v); if (rc2) return rc2; }
     // Dirichlet contacts (potential_solver.cpp:389-403 / potential_solver_gpu.cu:768-771)
     if (NL > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NL, 256), 256, 0, NL, -Vd / 2, d_site_potential_boundary);
     if (NR > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NR, 256), 256, 0, NR, Vd / 2, d_site_potential_boundary + (N - NR));
@@ -1784,16 +1909,18 @@ int dkmc_update_CB_edge_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, in
     int rc;
     if ((rc = ensure<double>(ctx, S_CG_VAL, (size_t)sp->nnz, &val))) return rc;
     if ((rc = ensure<double>(ctx, S_CG_RHS, m, &rhs))) return rc;
-    if ((rc = cg_workspace(ctx, m, sp->nnz, sp->d_row_ptr, &w))) return rc;
+    if ((rc = cg_workspace(ctx, m, sp->nnz, order_of(ctx, sp) ? order_of(ctx, sp)->rp2 : sp->d_row_ptr, &w))) return rc;
     DKMC_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
     // rule 1: high_G iff either site is a metal; the charges do not enter.  No cluster coarse space:
     // under this rule every strongly coupled set hangs on a Dirichlet contact through the metal layers.
     if ((rc = assemble_impl(ctx, sp, N, NL, NR, VL, VR, 1, high_G, low_G, d_site_element, nullptr, d_metals, num_metals, val,
                             rhs))) return rc;
+    SolveView v;
+    if ((rc = view_prepare(ctx, sp, NL, val, rhs, d_site_CB_edge, &w, &v))) return rc;
     DKMC_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
-    double *x = d_site_CB_edge + NL;
-    rc = solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, w, o, info);
+    rc = solve_refined(ctx, m, sp->nnz, v.rp, v.col, v.val, v.rhs, v.x, w, o, info);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
+    { int rc2 = view_finish(ctx, v); if (rc2) return rc2; }
     if (NL > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NL, 256), 256, 0, NL, VL, d_site_CB_edge);
     if (NR > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NR, 256), 256, 0, NR, VR, d_site_CB_edge + (N - NR));
     DKMC_CUDA(cudaEventRecord(ctx->ev_c, ctx->stream));
@@ -1807,6 +1934,54 @@ int dkmc_update_CB_edge_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N, in
     }
     if (rc == DKMC_ERR_NOT_CONVERGED) set_error("CG did not converge within max_iter=%d", o.max_iter);
     return rc;
+}
+
+int dkmc_solver_set_order(dkmc_ctx *ctx, const dkmc_sparsity *sp, const int *d_order) {
+    DKMC_REQUIRE(ctx && sp && sp->d_row_ptr && sp->d_col && sp->m > 0, "sparsity");
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_order(ctx);
+    if (d_order == nullptr) return DKMC_OK;
+    const int m = sp->m, nnz = sp->nnz;
+    SolverOrder *so = new SolverOrder();
+    ctx->solver_order = so;
+    DKMC_CUDA(cudaMalloc(&so->order, (size_t)m * sizeof(int)));
+    DKMC_CUDA(cudaMalloc(&so->inv, (size_t)m * sizeof(int)));
+    DKMC_CUDA(cudaMalloc(&so->rp2, ((size_t)m + 1) * sizeof(int)));
+    DKMC_CUDA(cudaMalloc(&so->col2, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int)));
+    DKMC_CUDA(cudaMalloc(&so->map, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int)));
+    DKMC_CUDA(cudaMemcpyAsync(so->order, d_order, (size_t)m * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    DKMC_CUDA(cudaMemsetAsync(so->inv, 0xff, (size_t)m * sizeof(int), ctx->stream));
+    int *tmp;   // row lengths [m] | bad [1] | scan scratch
+    int rc;
+    const size_t scan_tmp = (size_t)ceil_div(m, kScanTile) + 1;
+    if ((rc = ensure<int>(ctx, S_ORD_TMP, (size_t)m + 1 + scan_tmp, &tmp))) return rc;
+    int *len2 = tmp, *bad = tmp + m, *scratch = tmp + m + 1;
+    DKMC_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+    DKMC_LAUNCH(ctx, order_invert_kernel, ceil_div(m, 256), 256, 0, m, so->order, so->inv, len2, sp->d_row_ptr, bad);
+    int h_bad = 0;
+    DKMC_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_bad != 0) {
+        free_order(ctx);
+        set_error("dkmc_solver_set_order: d_order is not a permutation of 0 .. m-1");
+        return DKMC_ERR_ARG;
+    }
+    DKMC_CUDA(cudaMemsetAsync(so->rp2, 0, sizeof(int), ctx->stream));
+    if ((rc = inclusive_scan<int>(ctx, len2, m, so->rp2 + 1, scratch))) return rc;
+    DKMC_LAUNCH(ctx, order_fill_kernel, ceil_div(m, 128), 128, 0, m, so->order, so->inv, sp->d_row_ptr, sp->d_col, so->rp2, so->col2,
+                so->map);
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    so->key_row_ptr = sp->d_row_ptr; so->m = m; so->nnz = nnz;
+    return DKMC_OK;
+}
+
+int dkmc_solver_csr(dkmc_ctx *ctx, const dkmc_sparsity *sp, const int **d_row_ptr, const int **d_col, const int **d_order) {
+    DKMC_REQUIRE(ctx && sp && d_row_ptr && d_col, "null pointer");
+    SolverOrder *so = order_of(ctx, sp);
+    *d_row_ptr = so ? so->rp2 : sp->d_row_ptr;
+    *d_col = so ? so->col2 : sp->d_col;
+    if (d_order) *d_order = so ? so->order : nullptr;
+    return DKMC_OK;
 }
 
 int dkmc_spmv_tile_nnz(void) { return kSpmvTile; }
@@ -1994,15 +2169,16 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
     int rc;
     if ((rc = ensure<double>(ctx, S_CG_VAL, (size_t)sp->nnz, &val))) return rc;
     if ((rc = ensure<double>(ctx, S_CG_RHS, m, &rhs))) return rc;
-    if ((rc = cg_workspace(ctx, m, sp->nnz, sp->d_row_ptr, &d.w))) return rc;
+    if ((rc = cg_workspace(ctx, m, sp->nnz, order_of(ctx, sp) ? order_of(ctx, sp)->rp2 : sp->d_row_ptr, &d.w))) return rc;
     DKMC_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
     // replicated: assembly of all rows and the cluster detection (sub-millisecond)
     if ((rc = dkmc_assemble_K(ctx, sp, N, NL, NR, Vd, high_G, low_G, d_site_element, d_site_charge, d_metals, num_metals, val, rhs))) return rc;
     d.n_cl = 0;
     d.seg_start = d.seg_len = d.mem_row = nullptr;
+    SolveView v;
+    if ((rc = view_prepare(ctx, sp, NL, val, rhs, d_site_potential_boundary, &d.w, &v))) return rc;
     if (o.cluster_precond) {
-        const unsigned char *cls = static_cast<const unsigned char *>(ctx->slot_ptr[S_CLASS]);
-        if ((rc = build_clusters(ctx, m, NL, cls, sp->d_row_ptr, sp->d_col, val, &d.w))) return rc;
+        if ((rc = build_clusters(ctx, m, v.NL, v.cls, v.rp, v.col, v.val, &d.w))) return rc;
         d.n_cl = d.w.n_cl;
         d.seg_start = d.w.P.seg_start; d.seg_len = d.w.P.seg_len; d.mem_row = d.w.P.mem_row;
     }
@@ -2013,8 +2189,8 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
     {
         const int T = kSpmvTile;
         int h[2];
-        DKMC_CUDA(cudaMemcpyAsync(&h[0], sp->d_row_ptr + d.ra, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        DKMC_CUDA(cudaMemcpyAsync(&h[1], sp->d_row_ptr + d.rb, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        DKMC_CUDA(cudaMemcpyAsync(&h[0], v.rp + d.ra, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        DKMC_CUDA(cudaMemcpyAsync(&h[1], v.rp + d.rb, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
         // tile t holds the rows whose first non-zero index lies in [t*T, (t+1)*T)
         d.t0 = h[0] / T;
@@ -2025,8 +2201,8 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
     // fallback path with open peer windows: the search direction lives in this rank's window (offset 0), where
     // the neighbours' p2p_halo_kernel pushes their boundary rows (the persistent PCG keeps u there instead)
     if (ds->p2p && m <= ds->m_cap && !use_persistent_pcg(ctx)) d.w.p = reinterpret_cast<double *>(ds->win);
-    double *x = d_site_potential_boundary + NL;
-    rc = dist_solve_refined(ctx, m, sp->nnz, sp->d_row_ptr, sp->d_col, val, rhs, x, d, o, info);
+    double *x = v.x;
+    rc = dist_solve_refined(ctx, m, sp->nnz, v.rp, v.col, v.val, v.rhs, x, d, o, info);
     if (rc != DKMC_OK && rc != DKMC_ERR_NOT_CONVERGED) return rc;
     // all-gather of the solution.  Peer memory: own rows into the window, a barrier, every rank pulls
     // the other ranks' rows from their windows, a barrier (the windows are written again in the next solve)
@@ -2052,6 +2228,7 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
     }
     DKMC_NCCL(ncclGroupEnd());
     }
+    { int rc2 = view_finish(ctx, v); if (rc2) return rc2; }
     if (NL > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NL, 256), 256, 0, NL, -Vd / 2, d_site_potential_boundary);
     if (NR > 0) DKMC_LAUNCH(ctx, fill_kernel, ceil_div(NR, 256), 256, 0, NR, Vd / 2, d_site_potential_boundary + (N - NR));
     DKMC_CUDA(cudaEventRecord(ctx->ev_c, ctx->stream));

@@ -436,6 +436,12 @@ class GPUBuffers:
         e = [np.ascontiguousarray(r) for r in self.E_host]
         check(self.ctx.lib.dkmc_set_layer_energies(self.ctx.h, len(layers), *[a.ctypes.data_as(C.c_void_p) for a in e]))
         self._sparsity: Dict[tuple, Sparsity] = {}
+        self._host_xyz = (device.site_x, device.site_y, device.site_z)
+        # "auto": inputs whose interior sites are not already in x-major grid-cell order (the reference's order puts
+        # lattice atoms before interstitials) get that order INSIDE the solver; the public arrays keep the caller's
+        self.solver_order = getattr(device, "solver_order", "auto")
+        self.solver_order_applied = False
+        self._order_tensor = None
         # pinned staging buffers for the host<->device syncs
         self._pin = {}
 
@@ -447,6 +453,16 @@ class GPUBuffers:
             check(self.ctx.lib.dkmc_initialize_sparsity(self.ctx.h, self.N_, self.nn_, _ptr(self.neigh_idx), NL, NR,
                                                         C.byref(sp)))
             self._sparsity[key] = sp
+            if self.solver_order == "auto":
+                from . import structures
+                x, y, z = self._host_xyz
+                sl = slice(NL, self.N_ - NR)
+                order = structures.cell_order(x[sl], y[sl], z[sl], x0=float(x.min()))
+                if not np.array_equal(order, np.arange(len(order))):
+                    torch = _torch()
+                    self._order_tensor = torch.from_numpy(order.astype(np.int32)).to("cuda")
+                    check(self.ctx.lib.dkmc_solver_set_order(self.ctx.h, C.byref(sp), _ptr(self._order_tensor)))
+                    self.solver_order_applied = True
         return self._sparsity[key]
 
     _SYNCED = ("site_element", "site_charge", "site_potential_boundary", "site_potential_charge", "site_temperature")

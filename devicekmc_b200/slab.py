@@ -292,6 +292,7 @@ def bench_multi_gpu(args, metric: str, unit: str):
                 "ms_per_step": ms.item() / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "sites": s.dev.N, "nn": s.buf.nn_, "Vd": args.vd,
+                           "solver_order": "internal x-major cell order (input in the reference's site order)" if s.buf.solver_order_applied else "caller's (already x-major)",
                            "partition": f"x-slabs over {world} ranks: rows by nnz tiles (CG), targets by site (pairwise)",
                            "cg": ("slab-partitioned, exchange over NVLink peer memory (CUDA IPC)" if s.dcg is not None and s.dcg.p2p
                                   else "slab-partitioned, NCCL" if s.dcg is not None else "replicated"),

@@ -133,6 +133,19 @@ int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int
                                      double *d_site_potential_boundary,
                                      const dkmc_solver_opts *opts, dkmc_solve_info *info);
 
+/* Internal row order of the solver (optional; default: the caller's order).  The public arrays keep the
+ * caller's site order — the reference's puts all lattice atoms before all interstitials
+ * (reorder_boundary.py:113-124), so the CSR bandwidth is ~0.7 N and an index range is not a spatial slab.
+ * d_order[p] = the interior row (0 .. m-1, caller's numbering) that the solver puts at position p, e.g. the rows
+ * sorted x-major by grid cell (device array of sp->m ints, copied).  a4/a5/8f-3 then solve P K P^T: the structure
+ * is permuted once, the values (assembled in the caller's order: the diagonal keeps the reference's summation
+ * order), right-hand side and starting vector are gathered every step and the solution is scattered back.
+ * d_order = NULL removes the order.  dkmc_solver_csr: the CSR structure the solver really works on (for the
+ * slab plan of dkmc_dist_background_potential, whose row ranges then count internal rows). */
+int dkmc_solver_set_order(dkmc_ctx *ctx, const dkmc_sparsity *sp, const int *d_order);
+int dkmc_solver_csr(dkmc_ctx *ctx, const dkmc_sparsity *sp, const int **d_row_ptr, const int **d_col,
+                    const int **d_order);
+
 /* ---- conduction-band edge.  update_CB_edge_gpu_sparse, gpu_solvers.h:121-123
  * (potential_solver_gpu.cu:595-694; CPU semantics Device::setLaplacePotential,
  * potential_solver.cpp:4-139): the same Kirchhoff system with the rule "high_G iff either site is a

@@ -42,3 +42,12 @@ def test_multi_gpu_matches_single_gpu_1M(world):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     _run(world, "tiled_1M", 2, False, 29640 + world)
+
+
+@pytest.mark.parametrize("world,workload", [(2, "device_7.5nm"), (4, "crossbar_2x2")])
+def test_multi_gpu_shipped_structures_in_reference_order(world, workload):
+    """BASELINE configs 2 / 3: the shipped structures, sites in the reference's order — the slab plan counts the
+    solver's internal rows (dkmc_solver_set_order), so an index range is a slab although the input is not sorted"""
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run(world, workload, 2, workload == "device_7.5nm", 29660 + world)

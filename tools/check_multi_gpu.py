@@ -23,9 +23,10 @@ from devicekmc_b200 import slab  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="tiled_100k")
 ap.add_argument("--steps", type=int, default=3)
-ap.add_argument("--vd", type=float, default=10.0)
+ap.add_argument("--vd", type=float, default=None)
 ap.add_argument("--oracle", action="store_true")
 args = ap.parse_args()
+args.vd = bench.workload_vd(args.workload, args.vd)
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -61,6 +62,8 @@ for s in range(args.steps):
             o_c = max(o_c, float(np.abs(pc_m[r0:r0 + 512] - pc_o).max() / np.abs(pc_o).max()))
         good = good and o_b <= TOL and o_c <= TOL
         print(f"rank 0 step 0 vs ORACLE: phi_b rel {o_b:.2e} phi_c (3 bands) rel {o_c:.2e} {'OK' if o_b <= TOL and o_c <= TOL else 'MISMATCH'}", flush=True)
+    if args.oracle and s == 0:
+        dist.barrier()      # rank 0 spent seconds in the CPU oracle: the others wait here, not inside a kernel
     ok &= good
     print(f"rank {rank} step {s}: phi_b rel {e_b:.2e} phi_c rel {e_c:.2e} element== {same_el} charge== {same_q} "
           f"events {a['events']}/{b['events']} identical {same_ev} cg its {a['cg_iterations']}/{b['cg_iterations']} "
