@@ -40,6 +40,12 @@ def workload(name):
     return el, x, y, z, lat, nc, p
 
 
+def workload_config(name, sites, nn, Vd):
+    """the `config` object both arms print (same keys, same workload); arm-specific details go to `arm`"""
+    return {"workload": name, "sites": int(sites), "nn": int(nn), "Vd": float(Vd),
+            "l2": "inputs larger than L2 (matrix 12*nnz bytes, rate table 16*N*nn bytes)"}
+
+
 def workload_vd(name, vd):
     """the bias of a workload: --vd, else the V_switch of the structure's parameters.txt (10 V for the synthetic tiles)"""
     from devicekmc_b200 import structures as S
@@ -200,10 +206,12 @@ def cpu_step_sample(name, threads=None, pair_rows=None, Vd=10.0, events_per_step
         secs.append(t["charge"] + t["potential_boundary"] + t["pairwise_scaled"] + t["rate_table"] + t["event_loop_scaled"])
     t["init_neighbors"] = t_init
     t["warmup_potential_boundary_cold"] = warm["potential_boundary"]
-    sample = (f"oracle port, {len(secs)} warm step(s) of {name} after one untimed step (N={N}, N_charged={ncharged_last}, "
+    sample = (f"oracle port (the reference's algorithm: Jacobi-preconditioned CG on the sparse K, not the GPU arm's cluster "
+              f"coarse space), {len(secs)} warm step(s) of {name} after one untimed step (N={N}, N_charged={ncharged_last}, "
               f"{its_last} CG its from the previous potential); pairwise timed on {rows_used} of {N} target rows and scaled; "
               f"event loop timed on its first {int(t['events_sampled'])} events and scaled to {events_per_step} events per "
               f"step; all other stages in full")
+    t["_N"], t["_nn"] = N, nn
     return len(secs) / float(np.sum(secs)), threads, sample, t
 
 
@@ -212,12 +220,16 @@ def reference_arm(args):
     if rank != 0:
         return
     # a bounded run (~2 min on 16 cores): one untimed (cold) step, then at most 2 timed warm steps whatever --steps says
-    value, cores, smp, tim = cpu_step_sample(args.workload, events_per_step=args.events_per_step,
+    value, cores, smp, tim = cpu_step_sample(args.workload, Vd=args.vd, events_per_step=args.events_per_step,
                                              steps=max(1, min(args.steps, 2)))
+    N_, nn_ = tim.pop("_N"), tim.pop("_nn")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "Vd": 10.0},
+            "config": workload_config(args.workload, N_, nn_, args.vd),
+            "arm": {"events_per_step": args.events_per_step,
+                    "events_per_step_source": "median of what the GPU arm executes per step in the driver's window "
+                                              "(5 warm-up + 20 timed steps of tiled_1M at 10 V: 49)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": smp,
                              "stage_seconds": {k: round(v, 4) for k, v in tim.items()},
                              "why_port": "the reference CPU build needs a dense N x N K (8.5 TB at 1M sites)"},
@@ -424,13 +436,26 @@ def gpu_arm(args):
         "scan": {"bound": "hbm", "achieved": 16.0 * n_tab / (scan_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                  "frac": 16.0 * n_tab / (scan_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
     }
+    # one CG iteration inside a step (beside the pairwise sum): SURVEY 8d's 12 nnz + 92 m bytes over the measured
+    # time per iteration of the timed steps
+    its_total = max(1, int(np.sum([s["cg_iterations"] for s in stats])))
+    cg_us = 1e3 * float(np.sum([s["solve_ms"] for s in stats])) / its_total
+    cg_bytes = 12.0 * nnz + 92.0 * m
+    rooflines["cg_iteration"] = {"bound": "hbm", "achieved": cg_bytes / (cg_us * 1e-6) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": cg_bytes / (cg_us * 1e-6) / 1e9 / hbm_peak, "traffic": None, "bytes_per_iteration": cg_bytes,
+                                 "us_per_iteration": cg_us,
+                                 "note": "in-step: the persistent PCG shares the SMs with the pairwise sum (FP64 pipe)"}
     for k_, r_ in rooflines.items():
         r_["traffic"] = traffic.get(k_)
     # the contract counts 200 flop per pair; the kernel executes ~62 FP64 instructions per
     # pair, so `frac` > 1 is work saved, not a faster pipe: the pipe utilisation is the ncu figure
     rooflines["pairwise"]["fp64_pipe_active_pct_ncu"] = pipe_pct
-    rooflines["pairwise"]["note"] = ("achieved = 200 contract flop/pair / time; the kernel needs ~62 FP64 instructions "
-                                     "per pair, so frac > 1 is work saved; pipe utilisation = fp64_pipe_active_pct_ncu")
+    pf = C.c_longlong(-1)
+    check(lib.dkmc_pairwise_pairs_far(dev.ctx.h, C.byref(pf)))
+    rooflines["pairwise"]["pairs_far_field_formula"] = float(pf.value) if pf.value >= 0 else None
+    rooflines["pairwise"]["note"] = ("achieved = 200 contract flop/pair / time; the kernel needs ~40 FP64 instructions per "
+                                     "far-field pair (no square root, one division) and ~62 per near pair, so frac > 1 is work "
+                                     "saved; pipe utilisation = fp64_pipe_active_pct_ncu")
     dominant = max((k_ for k_ in shares if k_ != "potential"), key=shares.get)
     roof_key = {"pairwise": "pairwise", "cg_solve": "spmv_solver_order", "assemble": "spmv_solver_order", "rate_table": "rate_table",
                 "event_loop": "rate_table"}[dominant]
@@ -438,17 +463,19 @@ def gpu_arm(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, cores, smp, tim = cpu_step_sample(args.workload, events_per_step=int(np.median([s["events"] for s in stats])))
+        v, cores, smp, tim = cpu_step_sample(args.workload, Vd=Vd, events_per_step=int(np.median([s["events"] for s in stats])))
+        tim.pop("_N"); tim.pop("_nn")
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": smp,
                "stage_seconds": {k: round(t, 4) for k, t in tim.items()}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "sites": dev.N, "nn": buf.nn_, "interior_rows": m, "nnz": nnz,
-                       "n_charged": ncharged, "Vd": Vd, "overlap": "pairwise sum on a side stream, concurrent with the CG",
-                       "l2": "inputs larger than L2 (matrix 12*nnz bytes, rate table 16*N*nn bytes)",
-                       "init_seconds": round(init_s, 3)},
+            "config": workload_config(args.workload, dev.N, buf.nn_, Vd),
+            "arm": {"interior_rows": m, "nnz": nnz, "n_charged": ncharged, "init_seconds": round(init_s, 3),
+                    "overlap": "pairwise sum on a side stream, concurrent with the CG",
+                    "solver_order": ("internal x-major grid-cell order (input in the reference's site order)"
+                                     if buf.solver_order_applied else "caller's (already x-major by grid cell)")},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": buf.h2d_bytes(), "d2h_bytes_per_step": buf.d2h_bytes(),
                     "same_steps_as_value": bool(e2e_same)},
@@ -468,17 +495,27 @@ def main():
     ap.add_argument("--workload", default="tiled_1M")
     ap.add_argument("--vd", type=float, default=None, help="bias [V]; default: the workload's own (10 V for the synthetic tiles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--events-per-step", type=int, default=350,
-                    help="--impl reference: events per KMC step the bounded event-loop sample is scaled to (the mean of "
-                         "what the GPU arm executes in its five timed steps on tiled_1M: 799, 446, 249, 177, 85)")
+    ap.add_argument("--events-per-step", type=int, default=49,
+                    help="--impl reference: events per KMC step the bounded event-loop sample is scaled to (the median of "
+                         "what the GPU arm executes per step in the driver's 5 + 20 window on tiled_1M)")
     ap.add_argument("--replicated-cg", action="store_true",
                     help="N>1: every rank runs the whole CG beside its share of the pairwise sum, instead of the default "
                          "slab-partitioned CG whose per-iteration exchange goes through NVLink peer memory")
     ap.add_argument("--distributed-cg", action="store_true", help=argparse.SUPPRESS)  # the default since round 1
+    ap.add_argument("--ramp", action="store_true",
+                    help="BASELINE config 5: the I-V sweep through the reference's bias-point loop, weak scaling (the device grows "
+                         "with --gpus: ~0.5 M sites per GPU, 4 M sites at 8)")
+    ap.add_argument("--ramp-points", type=int, default=200)
+    ap.add_argument("--ramp-vmax", type=float, default=4.0)
+    ap.add_argument("--ramp-start", type=int, default=60, help="first bias point of the warm-up (point 60 of 200 = 2.4 V)")
+    ap.add_argument("--ramp-steps-per-point", type=int, default=1)
     args = ap.parse_args()
     args.vd = workload_vd(args.workload, args.vd)
     if args.impl == "reference":
         reference_arm(args)
+    elif args.ramp:
+        from devicekmc_b200 import slab
+        slab.bench_ramp(args, METRIC, UNIT)
     else:
         gpu_arm(args)
 

@@ -64,7 +64,7 @@ EXPORTS = [
     "dkmc_ctx_create", "dkmc_ctx_destroy", "dkmc_ctx_set_stream", "dkmc_ctx_synchronize",
     "dkmc_ctx_launch_count", "dkmc_set_layer_energies", "dkmc_neighbor_count", "dkmc_neighbor_fill", "dkmc_neighbor_table_host", "dkmc_snapshot_begin", "dkmc_snapshot_ready", "dkmc_snapshot_wait",
     "dkmc_initialize_sparsity", "dkmc_free_sparsity", "dkmc_update_charge", "dkmc_default_solver_opts",
-    "dkmc_background_potential_sparse", "dkmc_update_CB_edge_sparse", "dkmc_assemble_K", "dkmc_spmv", "dkmc_solve_cg", "dkmc_pcg_profile", "dkmc_ctx_set_legacy_cg", "dkmc_ctx_set_pcg_pipelined", "dkmc_solver_set_order", "dkmc_solver_csr",
+    "dkmc_background_potential_sparse", "dkmc_update_CB_edge_sparse", "dkmc_assemble_K", "dkmc_spmv", "dkmc_solve_cg", "dkmc_pcg_profile", "dkmc_ctx_set_legacy_cg", "dkmc_ctx_set_pcg_pipelined", "dkmc_solver_set_order", "dkmc_solver_csr", "dkmc_ctx_invalidate",
     "dkmc_poisson_gridless", "dkmc_poisson_gridless_rows", "dkmc_poisson_gridless_begin",
     "dkmc_poisson_gridless_join", "dkmc_ctx_set_pairwise_share", "dkmc_ctx_set_pairwise_cells", "dkmc_ctx_set_pairwise_cutoff", "dkmc_ctx_set_pairwise_incremental", "dkmc_pairwise_incremental_counts",
     "dkmc_pairwise_pairs_evaluated", "dkmc_ctx_set_pairwise_far_field", "dkmc_pairwise_pairs_far", "dkmc_build_event_list",

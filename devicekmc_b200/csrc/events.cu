@@ -27,6 +27,7 @@ constexpr int kRateWarps = 8;             // warps (= rows in flight) per rate-t
 constexpr int kLoopThreads = 1024;        // the persistent event-loop CTA
 constexpr int kMaxNN = 256;               // max neighbours per site supported by the loop
 constexpr int kHistBuckets = 2048;        // one per FP64 exponent
+constexpr int kTopCap = 1152;             // doubles of the prefix hierarchy's top levels kept in the loop's shared memory
 
 struct Levels {
     int n_levels;                          // level 0 = row sums (N entries)
@@ -200,15 +201,30 @@ __device__ __forceinline__ double ldv(const double *p) { return __ldcg(p); }
 __device__ __forceinline__ int ldi(const int *p) { return __ldcg(p); }
 
 // root-to-leaf walk by one warp.  out: idx (-1 = none), psum, flag (0 ok, 1 none, 2 needs exact)
-__device__ void select_walk(const LoopArgs &a, double u, const double *errA, const int *errB, int lane,
+// The top levels of the prefix hierarchy (1 + 32 + 1024 sums at 1 M sites) live in the loop's shared memory:
+// level `lev` >= top_lev is read and written there (s_top, offsets relative to level top_lev's), the lower ones in
+// global memory through L2 — three of the six dependent L2 round trips of a selection, and most of the re-scan.
+struct TopLevels {
+    double *s_top;
+    int top_lev;
+    long long top_off;
+};
+__device__ __forceinline__ double ld_level(const LoopArgs &a, const TopLevels &T, int lev, int idx) {
+    return lev >= T.top_lev ? T.s_top[a.lv.off[lev] - T.top_off + idx] : ldv(a.levels + a.lv.off[lev] + idx);
+}
+__device__ __forceinline__ void st_level(const LoopArgs &a, const TopLevels &T, int lev, int idx, double v) {
+    if (lev >= T.top_lev) T.s_top[a.lv.off[lev] - T.top_off + idx] = v;
+    else __stcg(a.levels + a.lv.off[lev] + idx, v);
+}
+
+__device__ void select_walk(const LoopArgs &a, const TopLevels &T, double u, const double *errA, const int *errB, int lane,
                             int &idx_out, double &psum_out, int &flag_out, double &delta_out) {
     const Levels &lv = a.lv;
     double prefix = 0.0, number = 0.0, psum = 0.0, delta = 0.0;
     int g = 0, flag = 0;
     for (int lev = lv.n_levels - 1; lev >= 0; --lev) {
-        const double *L = a.levels + lv.off[lev];
         int idx = g * 32 + lane;
-        double v = idx < lv.size[lev] ? ldv(L + idx) : 0.0;
+        double v = idx < lv.size[lev] ? ld_level(a, T, lev, idx) : 0.0;
         double inc = warp_inclusive_scan(v, lane);
         if (lev == lv.n_levels - 1) {
             psum = __shfl_sync(0xffffffffu, inc, 31);
@@ -382,8 +398,17 @@ __global__ void __launch_bounds__(kLoopThreads, 1) event_loop_kernel(LoopArgs a)
     __shared__ int s_rows[2 + 2 * kMaxNN];
     __shared__ int s_idx, s_flag, s_done, s_used, s_nev, s_nfb, s_nnone;
     __shared__ double s_psum, s_delta, s_time;
+    __shared__ double s_top[kTopCap];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = kLoopThreads / 32;
+    // the levels from top_lev up fit the shared copy (every level is padded to a multiple of 32 entries)
+    TopLevels T;
+    T.s_top = s_top;
+    T.top_lev = a.lv.n_levels;
+    const long long lv_end = a.lv.off[a.lv.n_levels - 1] + (a.lv.size[a.lv.n_levels - 1] + 31) / 32 * 32;
+    while (T.top_lev > 1 && lv_end - a.lv.off[T.top_lev - 1] <= kTopCap) --T.top_lev;
+    T.top_off = T.top_lev < a.lv.n_levels ? a.lv.off[T.top_lev] : lv_end;
+    for (long long k = tid; k < lv_end - T.top_off; k += kLoopThreads) s_top[k] = ldv(a.levels + T.top_off + k);
 
     // ---- error-bound tables from the exponent histogram
     for (int b = tid; b < kHistBuckets; b += kLoopThreads) errB[b] = a.hist[b];
@@ -433,7 +458,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) event_loop_kernel(LoopArgs a)
         if (warp == 0) {
             int idx, flag;
             double psum, delta;
-            select_walk(a, u1, errA, errB, lane, idx, psum, flag, delta);
+            select_walk(a, T, u1, errA, errB, lane, idx, psum, flag, delta);
             if (a.exact_mode == 1 && flag == 0) flag = 2;
             if (lane == 0) { s_idx = idx; s_flag = flag; s_psum = psum; s_delta = delta; }
         }
@@ -479,46 +504,98 @@ __global__ void __launch_bounds__(kLoopThreads, 1) event_loop_kernel(LoopArgs a)
             __syncthreads();
             // zero conflicting events (KMCProcess.cpp:330-352) and re-scan the touched rows
             double *rowsum = a.levels + a.lv.off[0];
-            for (int t = warp; t < n_touch; t += nwarps) {
-                const int r = s_rows[t];
-                if (r < 0) continue;
-                const size_t base = (size_t)r * a.nn;
-                double vals[8];
-                for (int k = 0; k < a.c; ++k) {
-                    int s = lane * a.c + k;
-                    double p = 0.0;
-                    if (s < a.nn) {
-                        p = ldv(a.ev_prob + base + s);
-                        // rows i and j go entirely (also when reached again as a neighbour row, so that
-                        // duplicate visits of a row write identical results)
-                        bool kill = (r == i || r == j);
-                        if (!kill) { int jj = ldi(a.neigh + base + s); kill = (jj == i || jj == j); }
-                        if (kill) {
-                            if (p != 0.0) __stcg(a.ev_prob + base + s, 0.0);
-                            __stcg(a.ev_type + base + s, (int)DKMC_NULL_EVENT);
-                            p = 0.0;
+            if (a.c <= 2) {
+                // two rows of a warp at a time, all their loads requested before the first is used (the rounds
+                // are independent: without this a warp pays one L2 round trip per row)
+                for (int t0 = warp; t0 < n_touch; t0 += 2 * nwarps) {
+                    double pv[2][2];
+                    int jv[2][2], rr[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int t = t0 + h * nwarps;
+                        rr[h] = t < n_touch ? s_rows[t] : -1;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int sl = lane * a.c + k;
+                            const bool ok = rr[h] >= 0 && k < a.c && sl < a.nn;
+                            pv[h][k] = ok ? ldv(a.ev_prob + (size_t)rr[h] * a.nn + sl) : 0.0;
+                            jv[h][k] = ok ? ldi(a.neigh + (size_t)rr[h] * a.nn + sl) : -1;
                         }
                     }
-                    vals[k] = p;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = rr[h];
+                        if (r < 0) continue;
+                        const size_t base = (size_t)r * a.nn;
+                        double vals[2] = {0.0, 0.0};
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int sl = lane * a.c + k;
+                            if (k < a.c && sl < a.nn) {
+                                double p = pv[h][k];
+                                // rows i and j go entirely (also when reached again as a neighbour row, so that
+                                // duplicate visits of a row write identical results)
+                                const bool kill = (r == i || r == j) || jv[h][k] == i || jv[h][k] == j;
+                                if (kill) {
+                                    if (p != 0.0) __stcg(a.ev_prob + base + sl, 0.0);
+                                    __stcg(a.ev_type + base + sl, (int)DKMC_NULL_EVENT);
+                                    p = 0.0;
+                                }
+                                vals[k] = p;
+                            }
+                        }
+                        double lane_sum;
+                        double inc = row_scan(vals, a.c, lane, lane_sum);
+                        if (lane == 31) __stcg(rowsum + r, inc);
+                    }
                 }
-                double lane_sum;
-                double inc = row_scan(vals, a.c, lane, lane_sum);
-                if (lane == 31) __stcg(rowsum + r, inc);
-            }
-            __syncthreads();
-            // propagate upwards: re-scan every touched group, level by level
-            for (int lev = 1; lev < a.lv.n_levels; ++lev) {
-                const double *child = a.levels + a.lv.off[lev - 1];
-                double *parent = a.levels + a.lv.off[lev];
-                const int csize = a.lv.size[lev - 1];
+            } else {
                 for (int t = warp; t < n_touch; t += nwarps) {
                     const int r = s_rows[t];
                     if (r < 0) continue;
-                    const int g = r >> (5 * lev);
-                    int ci = g * 32 + lane;
-                    double v = ci < csize ? ldv(child + ci) : 0.0;
-                    double inc = warp_inclusive_scan(v, lane);
-                    if (lane == 31) __stcg(parent + g, inc);
+                    const size_t base = (size_t)r * a.nn;
+                    double vals[8];
+                    for (int k = 0; k < a.c; ++k) {
+                        int s = lane * a.c + k;
+                        double p = 0.0;
+                        if (s < a.nn) {
+                            p = ldv(a.ev_prob + base + s);
+                            bool kill = (r == i || r == j);
+                            if (!kill) { int jj = ldi(a.neigh + base + s); kill = (jj == i || jj == j); }
+                            if (kill) {
+                                if (p != 0.0) __stcg(a.ev_prob + base + s, 0.0);
+                                __stcg(a.ev_type + base + s, (int)DKMC_NULL_EVENT);
+                                p = 0.0;
+                            }
+                        }
+                        vals[k] = p;
+                    }
+                    double lane_sum;
+                    double inc = row_scan(vals, a.c, lane, lane_sum);
+                    if (lane == 31) __stcg(rowsum + r, inc);
+                }
+            }
+            __syncthreads();
+            // propagate upwards: re-scan every touched group, level by level (a warp's groups all requested first)
+            for (int lev = 1; lev < a.lv.n_levels; ++lev) {
+                const int csize = a.lv.size[lev - 1];
+                for (int t0 = warp; t0 < n_touch; t0 += 4 * nwarps) {
+                    double v[4];
+                    int g[4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int t = t0 + h * nwarps;
+                        const int r = t < n_touch ? s_rows[t] : -1;
+                        g[h] = r >= 0 ? (r >> (5 * lev)) : -1;
+                        const int ci = g[h] * 32 + lane;
+                        v[h] = (g[h] >= 0 && ci < csize) ? ld_level(a, T, lev - 1, ci) : 0.0;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        if (g[h] < 0) continue;
+                        const double inc = warp_inclusive_scan(v[h], lane);
+                        if (lane == 31) st_level(a, T, lev, g[h], inc);
+                    }
                 }
                 __syncthreads();
             }
@@ -529,9 +606,14 @@ __global__ void __launch_bounds__(kLoopThreads, 1) event_loop_kernel(LoopArgs a)
             s_used += 2;
             if (idx >= 0) s_nev += 1; else s_nnone += 1;
             if (!(s_time < inv_freq)) s_done = 1;
+            // a rate overflowed (exp of a huge energy): the sum is inf or NaN, no entry can be selected and the drawn
+            // time is 0 for ever — stop with an error status instead of burning every batch of uniforms
+            if (!(s_psum == s_psum) || s_psum > 1.7e308) { s_done = 1; a.state->status = 1; }
         }
         __syncthreads();
     }
+    // the shared top levels back to global memory (continue calls, the tests' dkmc_last_event_tables)
+    for (long long k = tid; k < lv_end - T.top_off; k += kLoopThreads) __stcg(a.levels + T.top_off + k, s_top[k]);
     if (tid == 0) {
         a.state->event_time = s_time; a.state->psum_last = s_psum; a.state->delta_last = s_delta;
         a.state->n_events = s_nev; a.state->n_used = s_used; a.state->done = s_done;
@@ -643,6 +725,11 @@ static int run_loop(dkmc_ctx *ctx, const double *uniforms, int n_uniforms, int *
         info->n_exact_fallbacks = h.n_fallback;
         info->event_time = h.event_time;
     }
+    if (h.status != 0) {
+        ev.active = false;
+        set_error("event loop: the sum of the rates is not finite (a rate overflowed) after %d events", h.n_events);
+        return DKMC_ERR_ARG;
+    }
     if (!h.done) {
         set_error("event loop consumed all %d uniforms after %d events; call dkmc_kmc_step_continue", n_uniforms, h.n_events);
         return DKMC_ERR_RNG_EXHAUSTED;
@@ -707,6 +794,7 @@ int dkmc_execute_kmc_step(dkmc_ctx *ctx, int N, int nn, const int *d_neigh_idx, 
                      d_z && d_potential_boundary && d_potential_charge && d_site_element && d_site_charge,
                  "null pointer");
     DKMC_REQUIRE(N > 0 && nn > 0 && nn <= kMaxNN, "N > 0 and 0 < nn <= 256");
+    DKMC_REQUIRE((long long)N * nn < 2147483647ll, "N * nn must fit 32 bits: event indices are ints (about 41 M sites at nn = 52)");
     Levels lv;
     long long lv_total;
     int rc;

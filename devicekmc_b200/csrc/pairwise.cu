@@ -343,20 +343,33 @@ __global__ void __launch_bounds__(1024) pw_cell_scan_kernel(const PwGrid *__rest
     if (threadIdx.x == 0) cell_start[ncells] = carry_s;
 }
 
-// charged sites grouped by cell, ascending site index inside a cell (deterministic: the rank of an
-// entry is the number of EARLIER entries of the compacted, index-ordered list in the same cell)
+// charged sites grouped by cell, ascending site index inside a cell (deterministic): every entry takes the next
+// free slot of its cell (atomic cursor, arbitrary order), then one thread per cell sorts the cell's few entries
+// by site index.  (Round 1 ranked every entry against all earlier ones: O(n_charged^2).)
 __global__ void __launch_bounds__(256) pw_cell_fill_kernel(const int *__restrict__ n_src_ptr, const ChargedSite *__restrict__ src,
                                                            const int *__restrict__ src_idx, const int *__restrict__ cell_of,
-                                                           const int *__restrict__ cell_start, ChargedSite *__restrict__ out,
-                                                           int *__restrict__ out_idx) {
+                                                           const int *__restrict__ cell_start, int *__restrict__ cursor,
+                                                           ChargedSite *__restrict__ out, int *__restrict__ out_idx) {
     const int n = *n_src_ptr;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const int c = cell_of[e];
-        int rank = 0;
-        for (int j = 0; j < e; ++j) rank += (cell_of[j] == c) ? 1 : 0;
-        const int pos = cell_start[c] + rank;
+        const int pos = cell_start[c] + atomicAdd(cursor + c, 1);
         out[pos] = src[e];
         out_idx[pos] = src_idx[e];
+    }
+}
+__global__ void __launch_bounds__(128) pw_cell_sort_kernel(const PwGrid *__restrict__ gp, const int *__restrict__ cell_start,
+                                                           ChargedSite *__restrict__ out, int *__restrict__ out_idx) {
+    const int ncells = gp->ncx * gp->ncy * gp->ncz;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int a = cell_start[c], b = cell_start[c + 1];
+    for (int k = a + 1; k < b; ++k) {   // insertion sort by site index
+        const int key = out_idx[k];
+        const ChargedSite v = out[k];
+        int j = k;
+        while (j > a && out_idx[j - 1] > key) { out_idx[j] = out_idx[j - 1]; out[j] = out[j - 1]; --j; }
+        out_idx[j] = key; out[j] = v;
     }
 }
 
@@ -603,7 +616,9 @@ static int pairwise_bin_cells(dkmc_ctx *ctx, int N, const double *d_x, const dou
     if (grid_n > 1024) grid_n = 1024;
     DKMC_LAUNCH(ctx, pw_cell_count_kernel, grid_n, 256, 0, total, src, grid, cell_of, cell_count);
     DKMC_LAUNCH(ctx, pw_cell_scan_kernel, 1, 1024, 0, grid, cell_count, cell_start);
-    DKMC_LAUNCH(ctx, pw_cell_fill_kernel, grid_n, 256, 0, total, src, src_idx, cell_of, cell_start, out->src, out->src_idx);
+    DKMC_CUDA(cudaMemsetAsync(cell_count, 0, (kPwMaxCells + 1) * sizeof(int), ctx->stream));   // now the cells' fill cursors
+    DKMC_LAUNCH(ctx, pw_cell_fill_kernel, grid_n, 256, 0, total, src, src_idx, cell_of, cell_start, cell_count, out->src, out->src_idx);
+    DKMC_LAUNCH(ctx, pw_cell_sort_kernel, ceil_div(kPwMaxCells, 128), 128, 0, grid, cell_start, out->src, out->src_idx);
     out->grid = grid; out->cell_start = cell_start; out->pair_counter = pair_counter;
     return DKMC_OK;
 }

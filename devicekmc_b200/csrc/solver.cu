@@ -1504,6 +1504,19 @@ static int dist_halo_any(dkmc_ctx *ctx, const DistWork &d, double *v, CgScalars 
     return rc;
 }
 
+// the per-op peer-memory kernels record a wait that timed out in sc->pad: turn it into an error (and clear it, so
+// that one slow peer does not fail every later call)
+static int dist_check_pad(dkmc_ctx *ctx, CgScalars *sc, const char *what) {
+    int pad = 0;
+    DKMC_CUDA(cudaMemcpyAsync(&pad, &sc->pad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (pad == 0) return DKMC_OK;
+    DKMC_CUDA(cudaMemsetAsync(&sc->pad, 0, sizeof(int), ctx->stream));
+    set_error("%s: a peer GPU did not answer within the time limit (peer-memory exchange, code %d): the gathered rows are "
+              "incomplete", what, pad);
+    return DKMC_ERR_CUDA;
+}
+
 static int dist_grid(const dkmc_ctx *ctx, int n) {
     int g = ceil_div(n > 0 ? n : 1, kVecThreads);
     int cap = ctx->num_sms * 8;
@@ -1984,6 +1997,16 @@ int dkmc_solver_csr(dkmc_ctx *ctx, const dkmc_sparsity *sp, const int **d_row_pt
     return DKMC_OK;
 }
 
+int dkmc_ctx_invalidate(dkmc_ctx *ctx) {
+    DKMC_REQUIRE(ctx != nullptr, "ctx");
+    DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->tiling.d_tile_row) { cudaFree(ctx->tiling.d_tile_row); ctx->tiling.d_tile_row = nullptr; }
+    ctx->tiling.row_ptr = nullptr; ctx->tiling.m = 0; ctx->tiling.nnz = 0;
+    ctx->pw_grid.d_x = nullptr; ctx->pw_grid.d_sigma = nullptr; ctx->pw_grid.N = 0;
+    ctx->pw_inc.valid = false; ctx->pw_inc.since_full = 0;
+    return DKMC_OK;
+}
+
 int dkmc_spmv_tile_nnz(void) { return kSpmvTile; }
 
 int dkmc_ctx_set_legacy_cg(dkmc_ctx *ctx, int on) {
@@ -2122,7 +2145,7 @@ int dkmc_dist_allgather_rows(dkmc_ctx *ctx, double *d_buf, int n, const int *row
         for (int q = 0; q < ds->world; ++q) { R.begin[q] = row_begin[q]; R.end[q] = row_end[q]; }
         DKMC_LAUNCH(ctx, p2p_pull_rows_kernel, ctx->num_sms * 4, 256, 0, ds->peers, R, d_buf);
         if ((rc = dist_allreduce(ctx, scratch, 1, sc))) return rc;
-        return DKMC_OK;
+        return dist_check_pad(ctx, sc, "dkmc_dist_allgather_rows");
     }
     DKMC_NCCL(ncclGroupStart());
     for (int r = 0; r < ds->world; ++r) {
@@ -2220,6 +2243,7 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
         for (int q = 0; q < ds->world; ++q) { R.begin[q] = plan->row_begin[q]; R.end[q] = plan->row_end[q]; }
         DKMC_LAUNCH(ctx, p2p_pull_rows_kernel, ctx->num_sms * 4, 256, 0, ds->peers, R, x);
         if ((rc = dist_allreduce(ctx, d.red, 1, d.w.sc))) return rc;   // barrier
+        { int rcp = dist_check_pad(ctx, d.w.sc, "dkmc_dist_background_potential (all-gather of the solution)"); if (rcp) return rcp; }
     } else {
     DKMC_NCCL(ncclGroupStart());
     for (int r = 0; r < ds->world; ++r) {

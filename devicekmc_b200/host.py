@@ -501,6 +501,10 @@ class GPUBuffers:
         loop may mutate the site state) while the snapshot drains; Snapshot.write() produces the file
         Device::writeSnapshot would have written at this point."""
         torch = _torch()
+        # the previous snapshot's writer thread formats its file from the shared staging buffers: let it finish
+        last = getattr(self, "_last_snapshot", None)
+        if last is not None and last._thread is not None and last._thread.is_alive():
+            last._thread.join()
         if "snap" not in self._pin:
             self._pin["snap"] = (torch.empty(self.N_, dtype=torch.int32).pin_memory(),
                                  torch.empty(self.N_, dtype=torch.int32).pin_memory(),
@@ -509,7 +513,8 @@ class GPUBuffers:
         check(self.ctx.lib.dkmc_snapshot_begin(self.ctx.h, self.N_, _ptr(self.site_element), _ptr(self.site_charge),
                                                _ptr(self.site_potential_boundary), _ptr(self.site_potential_charge), None,
                                                _ptr(el), _ptr(q), _ptr(pot), None))
-        return Snapshot(self.ctx, device, el, q, pot)
+        self._last_snapshot = Snapshot(self.ctx, device, el, q, pot)
+        return self._last_snapshot
 
     def h2d_bytes(self) -> int:
         return self.N_ * (4 + 4 + 8 + 8 + 8)
@@ -541,15 +546,19 @@ class Snapshot:
         return self._el.numpy(), self._q.numpy(), self._pot.numpy()
 
     def write(self, filename: str, foldername: str = "."):
+        self._write(self.wait(), filename, foldername)
+
+    def _write(self, arrays, filename, foldername):
         import os
-        el, q, pot = self.wait()
+        el, q, pot = arrays
         d = self._dev
         write_snapshot(os.path.join(".", foldername, filename), el, d.site_x, d.site_y, d.site_z, pot)
 
     def write_async(self, filename: str, foldername: str = "."):
         """formats and writes the file on a host thread (the ctypes calls of the step release the GIL)"""
         import threading
-        self._thread = threading.Thread(target=self.write, args=(filename, foldername), daemon=True)
+        arrays = self.wait()     # the copies complete on the calling thread: only one thread talks to the context
+        self._thread = threading.Thread(target=self._write, args=(arrays, filename, foldername), daemon=True)
         self._thread.start()
         return self._thread
 

@@ -139,6 +139,10 @@ class SlabSim:
             share = tuple(int(v) for v in os.environ["DKMC_PW_SHARE"].split(","))
         from ._capi import check
         check(self.dev.ctx.lib.dkmc_ctx_set_pairwise_share(self.dev.ctx.h, share[0], share[1]))
+        self._share = list(share)
+        # the share follows the measured times (strong scaling shrinks the sum with N, weak scaling does not): one more
+        # CTA per SM when the sum ends after the CG, one fewer when it ends in less than half the CG's time
+        self._share_auto = not os.environ.get("DKMC_PW_SHARE") and not os.environ.get("DKMC_PW_SERIAL")
         self.dcg = None
         if distributed_cg and world > 1:
             from . import _dist
@@ -186,11 +190,64 @@ class SlabSim:
                 mine = self._pc_full[self.rank * self.chunk:(self.rank + 1) * self.chunk].clone()
                 self.dist.all_gather_into_tensor(self._pc_full, mine)
         t = self.sim.executeKMCStep(buf, dev, record_events=record_events)
-        return {"cg_iterations": info.iterations, "cg_converged": st == _capi.DKMC_OK, "cg_est_error": info.est_error,
+        if self._share_auto and info.iterations > 0:
+            want = self._share[0]
+            if pw_ms.value > 1.05 * info.solve_ms:
+                want = min(3, want + 1)
+            elif pw_ms.value < 0.5 * info.solve_ms:
+                want = max(1 if self.world > 1 else 2, want - 1)
+            if self.world > 1:      # every rank the same share: the slowest rank sets the pace
+                tw = self.torch.tensor([want], dtype=self.torch.int32, device="cuda")
+                self.dist.all_reduce(tw, op=self.dist.ReduceOp.MAX)
+                want = int(tw.item())
+            if want != self._share[0]:
+                self._share[0] = want
+                check(lib.dkmc_ctx_set_pairwise_share(dev.ctx.h, want, self._share[1]))
+        return {"cg_iterations": info.iterations, "pairwise_share": self._share[0], "cg_converged": st == _capi.DKMC_OK, "cg_est_error": info.est_error,
                 "solve_ms": info.solve_ms, "assemble_ms": info.assemble_ms,
                 "pairwise_ms": pw_ms.value,
                 "events": self.sim.last_info.n_events, "fallbacks": self.sim.last_info.n_exact_fallbacks,
                 "loop_ms": self.sim.last_info.loop_ms, "rate_ms": self.sim.last_info.rate_ms, "step_time": t}
+
+
+def iv_ramp(points: int = 200, v_max: float = 4.0) -> np.ndarray:
+    """the SET/RESET sweep of BASELINE config 5: 0 -> v_max -> 0 V in `points` bias points"""
+    up = points // 2
+    return np.concatenate([np.linspace(0.0, v_max, up, endpoint=False), np.linspace(v_max, 0.0, points - up)])
+
+
+def bias_loop(s: "SlabSim", V_switch, t_switch, max_steps_per_point=None, max_steps=None, scale_warm_start=True, on_step=None,
+              record_events: int = 0):
+    """The reference's bias-point loop (kmc_main.cpp:136-279) over a SlabSim (1 or N ranks): for every bias point
+    host -> device sync, then KMC steps (charge, potential at Vd, events) until kmc_time reaches t_switch, then
+    device -> host sync (where the reference writes its snapshot).  max_steps_per_point / max_steps bound the work
+    (the reference itself only stops when the physical time has elapsed: at a bias where the rates are high that
+    is ~1e11 steps per point).  scale_warm_start: the boundary potential is linear in Vd while the structure does
+    not change, so the previous solution is rescaled by Vd / Vd_prev before it starts the CG (the reference starts
+    from the unscaled previous potential, potential_solver_gpu.cu:754).  Returns the per-step stats."""
+    stats, total = [], 0
+    t_switch = np.broadcast_to(np.asarray(t_switch, float), (len(V_switch),))
+    vd_prev = None
+    for k, Vd in enumerate(V_switch):
+        s.buf.sync_HostToGPU(s.dev)                                     # kmc_main.cpp:172
+        kmc_time, count = 0.0, 0
+        while kmc_time < t_switch[k]:
+            if scale_warm_start and vd_prev not in (None, 0.0) and vd_prev != Vd:
+                s.buf.site_potential_boundary.mul_(float(Vd) / float(vd_prev))
+            vd_prev = float(Vd)
+            st = s.step(float(Vd), record_events=record_events)
+            st["Vd"], st["bias_point"] = float(Vd), k
+            stats.append(st)
+            if on_step:
+                on_step(st)
+            kmc_time += st["step_time"]
+            count += 1; total += 1
+            if (max_steps_per_point and count >= max_steps_per_point) or (max_steps and total >= max_steps):
+                break
+        s.buf.sync_GPUToHost(s.dev)                                     # kmc_main.cpp:282-286
+        if max_steps and total >= max_steps:
+            break
+    return stats
 
 
 def multi_vs_single_step(multi: "SlabSim", arrays, p, Vd: float) -> dict:
@@ -291,12 +348,12 @@ def bench_multi_gpu(args, metric: str, unit: str):
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms.item() / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "sites": s.dev.N, "nn": s.buf.nn_, "Vd": args.vd,
-                           "solver_order": "internal x-major cell order (input in the reference's site order)" if s.buf.solver_order_applied else "caller's (already x-major)",
-                           "partition": f"x-slabs over {world} ranks: rows by nnz tiles (CG), targets by site (pairwise)",
-                           "cg": ("slab-partitioned, exchange over NVLink peer memory (CUDA IPC)" if s.dcg is not None and s.dcg.p2p
-                                  else "slab-partitioned, NCCL" if s.dcg is not None else "replicated"),
-                           "l2": "inputs larger than L2"},
+                "config": bench.workload_config(args.workload, s.dev.N, s.buf.nn_, args.vd),
+                "arm": {"solver_order": "internal x-major cell order (input in the reference's site order)" if s.buf.solver_order_applied else "caller's (already x-major)",
+                        "partition": f"x-slabs over {world} ranks: rows by nnz tiles (CG), targets by site (pairwise)",
+                        "cg": ("slab-partitioned persistent PCG, exchange over NVLink peer memory (CUDA IPC)" if s.dcg is not None and s.dcg.p2p
+                               else "slab-partitioned, NCCL" if s.dcg is not None else "replicated"),
+                        "pairwise_share_ctas_per_sm": stats[-1].get("pairwise_share")},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": args.steps / (ms2.item() * 1e-3), "unit": unit, "h2d_bytes_per_step": s.buf.h2d_bytes(),
                         "d2h_bytes_per_step": s.buf.d2h_bytes()},
@@ -308,5 +365,76 @@ def bench_multi_gpu(args, metric: str, unit: str):
                 "per_step": {"events": [t["events"] for t in stats], "cg_iterations": [t["cg_iterations"] for t in stats]},
                 "pcg_profile": prof, "ranks_consistent": consistent, "ranks_state_sha256": digests[0][:16], "parity": parity,
                 "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+# weak scaling of BASELINE config 5: ~0.5 M sites per GPU (tiles of the 2.5 nm cell: ny x nz)
+RAMP_TILES = {1: (7, 8), 2: (10, 11), 4: (14, 15), 8: (21, 20)}
+
+
+def bench_ramp(args, metric: str, unit: str):
+    """bench.py --ramp [--gpus N]: the I-V sweep of BASELINE config 5 through the reference's bias-point loop
+    (bias_loop), weak scaling: the device grows with N (RAMP_TILES, ~0.5 M sites per GPU; N = 8 is the 4 M-site
+    device).  One KMC step per bias point (--ramp-steps-per-point), W untimed points, then K timed ones starting
+    at --ramp-start; value = KMC steps per second of the whole job."""
+    import torch
+    import torch.distributed as dist
+    import bench
+    from . import structures as S
+    from .host import KMCParameters
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29571")
+    os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ny, nz = RAMP_TILES[world]
+    el, x, y, z, lat, nc = S.tile_device(ny, nz)
+    p = KMCParameters(lattice=tuple(lat), num_atoms_contact=nc, num_atoms_first_layer=nc)
+    el = bench.substoichiometric(el, p)
+    s = SlabSim((el, x, y, z), p, rank, world)
+    ramp = iv_ramp(args.ramp_points, args.ramp_vmax)
+    a, w, k = args.ramp_start, args.warmup, args.steps
+    sampler = bench.ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    bias_loop(s, ramp[a:a + w], 1e-3, max_steps_per_point=args.ramp_steps_per_point)
+    launches0 = s.dev.ctx.launch_count()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    stats = bias_loop(s, ramp[a + w:a + w + k], 1e-3, max_steps_per_point=args.ramp_steps_per_point)
+    e1.record(); e1.synchronize()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = s.dev.ctx.launch_count() - launches0
+    import hashlib
+    digest = hashlib.sha256(s.buf.site_element.cpu().numpy().tobytes() + s.buf.site_charge.cpu().numpy().tobytes()).hexdigest()
+    digests = [None] * world
+    dist.all_gather_object(digests, digest)
+    if rank == 0:
+        clocks = sampler.stop()
+        n = len(stats)
+        med = lambda key: float(np.median([t[key] for t in stats]))
+        line = {"metric": metric, "value": n / (ms.item() * 1e-3), "unit": unit, "n_gpus": world, "steps": n, "warmup": w,
+                "ms_per_step": ms.item() / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"iv_ramp_{ny}x{nz}", "sites": s.dev.N, "sites_per_gpu": s.dev.N // world, "nn": s.buf.nn_,
+                           "ramp": f"0 -> {args.ramp_vmax} -> 0 V in {args.ramp_points} bias points, t_switch 1e-3 s, through the "
+                                   f"reference's bias-point loop (kmc_main.cpp:136-279); bias points {a + w} .. {a + w + k - 1}",
+                           "Vd_first_last": [float(stats[0]["Vd"]), float(stats[-1]["Vd"])],
+                           "steps_per_bias_point": args.ramp_steps_per_point, "l2": "inputs larger than L2"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": n / (ms.item() * 1e-3), "unit": unit,
+                        "h2d_bytes_per_step": s.buf.h2d_bytes() // args.ramp_steps_per_point,
+                        "d2h_bytes_per_step": s.buf.d2h_bytes() // args.ramp_steps_per_point,
+                        "note": "the bias-point loop itself moves the site arrays host -> device and back at every bias point "
+                                "(kmc_main.cpp:172,282): the timed region includes those copies"},
+                "stage_ms": {"cg_solve": med("solve_ms"), "pairwise_concurrent": med("pairwise_ms"), "assemble": med("assemble_ms"),
+                             "rate_table": med("rate_ms"), "event_loop": med("loop_ms")},
+                "per_step": {"Vd": [round(t["Vd"], 4) for t in stats], "events": [t["events"] for t in stats],
+                             "cg_iterations": [t["cg_iterations"] for t in stats]},
+                "ranks_consistent": len(set(digests)) == 1, "roofline": None, "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()

@@ -133,6 +133,14 @@ int dkmc_background_potential_sparse(dkmc_ctx *ctx, const dkmc_sparsity *sp, int
                                      double *d_site_potential_boundary,
                                      const dkmc_solver_opts *opts, dkmc_solve_info *info);
 
+/* The context caches a few things keyed by the ADDRESS of the caller's arrays: the SpMV tiling (by d_row_ptr, m,
+ * nnz), the cell grid of the pairwise sum (by d_x, d_sigma, N: positions and sigma are static in the reference),
+ * the previous charges of the opt-in incremental pairwise update (by d_site_charge / d_site_potential_charge).
+ * A caller that changes such an array IN PLACE (another structure at the same address, positions moved, phi_c
+ * overwritten by a restart) calls dkmc_ctx_invalidate: the next calls rebuild them.  Matrix VALUES are never
+ * cached: dkmc_spmv / dkmc_solve_cg read the val array they are given. */
+int dkmc_ctx_invalidate(dkmc_ctx *ctx);
+
 /* Internal row order of the solver (optional; default: the caller's order).  The public arrays keep the
  * caller's site order — the reference's puts all lattice atoms before all interstitials
  * (reorder_boundary.py:113-124), so the CSR bandwidth is ~0.7 N and an index range is not a spatial slab.
@@ -260,7 +268,8 @@ typedef struct {
     int n_events;          /* events executed in this step */
     int n_used;            /* uniforms consumed */
     int n_exact_fallbacks; /* selections decided by the exact sequential replay */
-    double event_time;     /* the last residence-time draw (what the reference returns) */
+    double event_time;     /* the last residence-time draw (what the reference returns): -ln(u2) / Psum with the
+                              hierarchical Psum (the reference's is the sequential sum: equal to ~1e-15 relative) */
     double rate_ms, loop_ms;
 } dkmc_step_info;
 int dkmc_execute_kmc_step(dkmc_ctx *ctx, int N, int nn, const int *d_neigh_idx, const int *d_site_layer,

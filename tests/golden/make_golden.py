@@ -22,6 +22,10 @@ rnd_seed_kmc = 1, CPU build, 1 process):
   s_traj_6V_pbc.npz  the same at constant 6 V with pbc = 1 (periodic in y and z), 4 KMC steps
   s_snapshot.npz   Device::writeSnapshot (Device.cpp:236-252) of the s_step0 state: sha256 and size of the
                    file, its first and last lines
+  s_tile28k.npz    SURVEY 8c's "~25 k-site tile": the base cell tiled 1 x 3 (28 197 sites, the reference's site order
+                   copy after copy), where the reference's dense K (6.4 GB) and dgesv still run: element after the
+                   reference's own 5 % draw, charges, phi_b at 6 V (dense LU), phi_c — pins the sparse oracle and the
+                   GPU path against the reference beyond the 9 k-site cell, on a state with uncharged-vacancy clusters
   s_cb_edge.npz    Device::setLaplacePotential (CPU branch, potential_solver.cpp:4-139) at Vd = 1.5 V:
                    site_CB_edge of all sites
 """
@@ -54,6 +58,39 @@ def new_sim(pbc=0):
         f.write(txt); f.close()
         params = f.name
     return R.RefSim(params, REF + "reordered_device_2.5.xyz")
+
+
+def tile28k():
+    import re
+    import tempfile
+    from devicekmc_b200 import structures as S
+    from devicekmc_b200.host import write_xyz
+    el, x, y, z, lat, nc = S.tile_device(1, 3, order="tile")
+    d = tempfile.mkdtemp()
+    xyz = os.path.join(d, "tile_1x3.xyz")
+    write_xyz(xyz, el, x, y, z)
+    txt = open(REF + "parameters.txt").read()
+    txt, n1 = re.subn(r"lattice = [^\n/]*", "lattice = %r %r %r " % (lat[0], lat[1], lat[2]), txt, count=1)
+    txt, n2 = re.subn(r"num_atoms_first_layer = \d+", "num_atoms_first_layer = %d" % nc, txt, count=1)
+    txt, n3 = re.subn(r"num_atoms_contact = \d+", "num_atoms_contact = %d" % nc, txt, count=1)
+    assert n1 == n2 == n3 == 1
+    par = os.path.join(d, "parameters.txt")
+    open(par, "w").write(txt)
+    s = R.RefSim(par, xyz)
+    assert s.N == len(x) and s.num_atoms_contact == nc
+    nb = s.neigh_idx()
+    el1 = s.element()
+    s.update_charge()
+    q = s.charge()
+    Vd = 6.0
+    s.background_potential(Vd)
+    s.poisson_gridless()
+    pb, pc = s.potential_boundary(), s.potential_charge()
+    np.savez_compressed(os.path.join(OUT, "s_tile28k.npz"), N=s.N, nn=s.nn, Vd=Vd, n_contact=nc, lattice=s.lattice,
+                        neigh_sha=sha(nb), element=el1.astype(np.int8), charge=q.astype(np.int8), potential_boundary=pb,
+                        potential_charge=pc)
+    print("s_tile28k: N", s.N, "nn", s.nn, "charged", int((q != 0).sum()))
+    s.close()
 
 
 def step0():
@@ -190,6 +227,9 @@ if __name__ == "__main__":
     import devicekmc_b200.host as H
     p = H.KMCParameters.from_file(REF + "parameters.txt")
     which = sys.argv[1:] or ["step0", "ramp", "6V", "10V", "6V_pbc", "cb_edge", "snapshot", "rates_ions", "substoich"]
+    if "tile28k" in which:
+        # ~25 minutes and ~7 GB: the reference's O(N^2) set-up, dense 27 333^2 K and dgesv at 28 k sites
+        tile28k()
     if "step0" in which:
         step0()
     if "substoich" in which:

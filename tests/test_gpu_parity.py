@@ -487,6 +487,36 @@ def test_trajectory_matches_reference(base_case, torch, name):
     assert np.array_equal(buf.site_element.cpu().numpy(), g["element_last"].astype(np.int32))
 
 
+def test_bias_point_loop_reproduces_the_reference_run(torch):
+    """BASELINE config 1 through the bias-point loop (kmc_main.cpp:136-279): the shipped 500-point ramp
+    (0 -> 12 V, t_switch 1e-3 s), 100 KMC steps — the same bias point for every step, the same events and the same
+    KMC times as the reference's CPU run (s_traj_ramp100.npz), with the warm start rescaled by Vd / Vd_prev"""
+    from conftest import GOLDEN
+    import bench
+    from devicekmc_b200 import slab, structures as S
+    from devicekmc_b200.host import KMCParameters
+    g = np.load(os.path.join(GOLDEN, "s_traj_ramp100.npz"))
+    el, x, y, z, lat, nc = S.load_base_cell()
+    p = KMCParameters(lattice=tuple(lat), num_atoms_contact=nc, num_atoms_first_layer=nc)
+    el = bench.substoichiometric(el, p)
+    sim = slab.SlabSim((el, x, y, z), p, 0, 1)
+    V_switch = np.linspace(0.0, 12.0, 500)          # test_2.5nm/parameters.txt:41
+    seen = []
+
+    def on_step(st):
+        seen.append((st["Vd"], sim.sim.last_events[:, 1:3].copy(), st["step_time"], st["cg_converged"]))
+    n = len(g["Vd"])
+    slab.bias_loop(sim, V_switch, 1e-3, max_steps=n, on_step=on_step, record_events=65536)
+    assert len(seen) == n
+    for s_, (Vd, ev, t, conv) in enumerate(seen):
+        assert conv
+        assert abs(Vd - float(g["Vd"][s_])) <= 1e-12, f"step {s_}: bias point"
+        ev_ref = g["ev_ij"][g["ev_ptr"][s_]:g["ev_ptr"][s_ + 1]]
+        assert np.array_equal(ev, ev_ref), f"step {s_}: executed events differ"
+        assert abs(t - g["step_time"][s_]) <= 1e-7 * abs(g["step_time"][s_]), f"step {s_}"
+    assert np.array_equal(sim.buf.site_element.cpu().numpy(), g["element_last"].astype(np.int32))
+
+
 # ------------------------------------------------------------------ 8f-4 snapshots that do not stall the step
 def test_snapshot_is_a_consistent_copy_while_the_step_goes_on(base_case, golden_step0, torch, tmp_path):
     import hashlib
