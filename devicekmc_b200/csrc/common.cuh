@@ -111,7 +111,7 @@ struct dkmc_ctx {
         const int *d_charge = nullptr;
         double *d_out = nullptr;
     } pw_pending;
-    int pcg_pipelined = -1;          // persistent PCG: pipelined recurrences (one synchronisation per iteration); -1 = on several GPUs
+    int pcg_pipelined = -1;          // persistent PCG: pipelined recurrences (one synchronisation per iteration); -1 = from four GPUs on
     int pw_far_field = 1;            // cell-list kernel: far-field formula for the runs beyond t = kErfcFarT0
     int pw_use_cells = 1;            // skip sources beyond the distance where erfc is exactly 0 (non-periodic devices)
     struct { const double *d_x = nullptr, *d_sigma = nullptr; const void *box = nullptr; int N = 0; double cutoff_sigmas = 0.0; } pw_grid;

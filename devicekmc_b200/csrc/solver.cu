@@ -1038,7 +1038,9 @@ static int run_pcg_persistent(dkmc_ctx *ctx, int m, const int *d_row_ptr, const 
     // above the floor of the pipelined recurrences): the first solve of a step runs to 1e-12, where the pipelined
     // recurrence residual stagnates in about one step out of six (measured, 1 M sites) — and the restarts are two
     // thirds of a step's iterations.
-    const bool want = (ctx->pcg_pipelined < 0 ? geo.peers.world > 1 : ctx->pcg_pipelined != 0) && tol >= 1e-8;
+    // auto: from four GPUs on (at two the hidden round trip is worth less than the restarts' extra iterations:
+    // 42.3 against 44.3 KMC steps/s at 1 M sites)
+    const bool want = (ctx->pcg_pipelined < 0 ? geo.peers.world >= 4 : ctx->pcg_pipelined != 0) && tol >= 1e-8;
     int done_its = 0;
     if (want && w.P.pos != nullptr) {
         int fallback = 0;

@@ -328,7 +328,7 @@ int dkmc_dist_background_potential(dkmc_ctx *ctx, const dkmc_sparsity *sp, int N
 /* on = 1: run the CG as one kernel per operation with host convergence polls (the round-1 path, kept as the
  * A/B baseline and as the fallback without peer access); default 0 (env DKMC_LEGACY_CG=1 sets it at create). */
 int dkmc_ctx_set_legacy_cg(dkmc_ctx *ctx, int on);
-/* The persistent-kernel CG comes in two recurrences.  on = 1 (the default on several GPUs): pipelined CG — both inner products of an
+/* The persistent-kernel CG comes in two recurrences.  on = 1 (the default from four GPUs on, for the restarts' correction solves): pipelined CG — both inner products of an
  * iteration are taken before its matrix product, so their (cross-GPU) reduction travels while the product runs
  * and an iteration has ONE synchronisation point.  on = 0: Chronopoulos-Gear CG, two synchronisation points per
  * iteration (the default on one GPU, where there is no NVLink round trip to hide; also the automatic fall-back

@@ -35,8 +35,21 @@ def step():
 for _ in range(args.warm):
     step()
 torch.cuda.synchronize()
+# one public SpMV launch on the step's matrix (spmv_tile_kernel<0>: the SpMV roofline's kernel; inside a step the
+# same tile code runs as a phase of the persistent PCG kernel)
+import ctypes as C  # noqa: E402
+from devicekmc_b200._capi import check  # noqa: E402
+sp = buf.sparsity(nc, nc)
+val = torch.empty(sp.nnz, dtype=torch.float64, device="cuda"); rhs = torch.empty(sp.m, dtype=torch.float64, device="cuda")
+check(dev.ctx.lib.dkmc_assemble_K(dev.ctx.h, C.byref(sp), dev.N, nc, nc, args.vd, p.high_G, p.low_G, buf.site_element.data_ptr(),
+                                  buf.site_charge.data_ptr(), buf.metal_types.data_ptr(), len(p.metals), val.data_ptr(), rhs.data_ptr()))
+xv = torch.rand(sp.m, dtype=torch.float64, device="cuda"); yv = torch.empty_like(xv)
+for _ in range(3):
+    check(dev.ctx.lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xv.data_ptr(), yv.data_ptr()))
+torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
 out = step()
+check(dev.ctx.lib.dkmc_spmv(dev.ctx.h, sp.m, sp.nnz, sp.d_row_ptr, sp.d_col, val.data_ptr(), xv.data_ptr(), yv.data_ptr()))
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("profiled step:", out, "events", sim.last_info.n_events)

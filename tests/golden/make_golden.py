@@ -70,7 +70,7 @@ def tile28k():
     xyz = os.path.join(d, "tile_1x3.xyz")
     write_xyz(xyz, el, x, y, z)
     txt = open(REF + "parameters.txt").read()
-    txt, n1 = re.subn(r"lattice = [^\n/]*", "lattice = %r %r %r " % (lat[0], lat[1], lat[2]), txt, count=1)
+    txt, n1 = re.subn(r"lattice = [^\n/]*", "lattice = %r %r %r " % (float(lat[0]), float(lat[1]), float(lat[2])), txt, count=1)
     txt, n2 = re.subn(r"num_atoms_first_layer = \d+", "num_atoms_first_layer = %d" % nc, txt, count=1)
     txt, n3 = re.subn(r"num_atoms_contact = \d+", "num_atoms_contact = %d" % nc, txt, count=1)
     assert n1 == n2 == n3 == 1

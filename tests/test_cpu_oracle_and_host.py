@@ -339,3 +339,39 @@ def test_product_path_fails_loudly_without_gpu():
     src = "".join(open(os.path.join(ROOT, "devicekmc_b200", f)).read() for f in ("host.py", "_capi.py", "structures.py", "slab.py")
                   if os.path.exists(os.path.join(ROOT, "devicekmc_b200", f)))
     assert "oracle" not in src.replace("# oracle", ""), "the product path must never import the oracle"
+
+
+def test_oracle_matches_reference_build_on_the_28k_tile():
+    """the sparse oracle pinned against the reference's own CPU build beyond the 9 k-site cell — the base
+    cell tiled 1 x 3 (28 197 sites, the largest the reference's dense K + dgesv handles comfortably here), state
+    with uncharged-vacancy clusters, 6 V.  Integers bit-exact; phi_c bit-exact; phi_b to what the reference's LU
+    itself delivers (its dgesv is ~1e-9 off its own matrix, see test_background_potential_matches_reference)."""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "s_tile28k.npz")
+    if not os.path.exists(path):
+        pytest.skip("s_tile28k.npz not generated (tests/golden/make_golden.py tile28k)")
+    import hashlib
+    from oracle import oracle as O
+    from devicekmc_b200 import structures as S
+    from devicekmc_b200.host import KMCParameters, VACANCY
+    g = np.load(path)
+    el0, x, y, z, lat, nc = S.tile_device(1, 3, order="tile")
+    assert len(x) == int(g["N"]) == 28197 and nc == int(g["n_contact"])
+    p = KMCParameters(lattice=tuple(lat), num_atoms_contact=nc, num_atoms_first_layer=nc)
+    nb, nn = O.neighbor_list(x, y, z, lat, p.pbc, p.nn_dist, method=1)
+    assert nn == int(g["nn"])
+    assert hashlib.sha256(np.ascontiguousarray(nb).tobytes()).hexdigest() == str(g["neigh_sha"])
+    el = g["element"].astype(np.int32)                      # after the reference's own 5 % draw
+    import bench
+    assert np.array_equal(bench.substoichiometric(el0, p), el)
+    q = O.update_charge(nb, el, p.metals, np.zeros(len(x), np.int32))
+    assert np.array_equal(q, g["charge"].astype(np.int32))
+    unch = (el == VACANCY) & (q == 0)
+    clustered = unch & np.where(nb >= 0, unch[np.clip(nb, 0, None)], False).any(axis=1)
+    assert clustered.sum() >= 4                             # the state the cluster coarse space exists for
+    Vd = float(g["Vd"])
+    pb, _ = O.background_potential(nb, nc, nc, el, q, p.metals, p.high_G, p.low_G, Vd, refine=3)
+    assert np.abs(pb - g["potential_boundary"]).max() <= 5e-9 * np.abs(g["potential_boundary"]).max()
+    pc = O.poisson_gridless(x, y, z, lat, p.pbc, q, p.sigma, p.k)
+    assert np.array_equal(pc, g["potential_charge"])

@@ -144,3 +144,36 @@ def test_crossbar_2x2_potential_residual_and_order(torch):
     pb = buf.site_potential_boundary
     assert float(pb.max()) <= Vd / 2 * (1 + 1e-12) and float(pb.min()) >= -Vd / 2 * (1 + 1e-12)
     assert torch.all(pb[:nc] == -Vd / 2) and torch.all(pb[-nc:] == Vd / 2)
+
+
+def test_28k_tile_matches_the_reference_build(O, torch):
+    """the GPU path against the reference's own CPU build at 28 k sites (s_tile28k.npz: dense K + dgesv), input in
+    the reference's site order copy after copy, state with uncharged-vacancy clusters"""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "s_tile28k.npz")
+    if not os.path.exists(path):
+        pytest.skip("s_tile28k.npz not generated")
+    import devicekmc_b200 as D
+    from devicekmc_b200 import structures as S
+    from devicekmc_b200.host import KMCParameters
+    g = np.load(path)
+    el0, x, y, z, lat, nc = S.tile_device(1, 3, order="tile")
+    p = KMCParameters(lattice=tuple(lat), num_atoms_contact=nc, num_atoms_first_layer=nc)
+    dev = D.Device([], p, arrays=(g["element"].astype(np.int32), x, y, z))
+    sim = D.KMCProcess(dev, p.freq)
+    buf = D.GPUBuffers(sim.layers, sim.site_layer, sim.freq, dev, p.metals)
+    buf.sync_HostToGPU(dev)
+    dev.updateCharge(buf, p.metals)
+    assert np.array_equal(buf.site_charge.cpu().numpy(), g["charge"].astype(np.int32))
+    out = dev.updatePotential(buf, p, float(g["Vd"]), n_contact=nc)
+    assert out["cg_converged"] and buf.solver_order_applied
+    ref_b, ref_c = g["potential_boundary"], g["potential_charge"]
+    # vs the reference's dgesv (1e-9 off its own matrix) and, tighter, vs the oracle
+    assert rel_inf(buf.site_potential_boundary.cpu().numpy(), ref_b) <= 5e-9
+    nb = dev.neigh_idx.reshape(dev.N, -1)
+    q = buf.site_charge.cpu().numpy()
+    pb_o, _ = O.background_potential(nb, nc, nc, dev.site_element, q, p.metals, p.high_G, p.low_G, float(g["Vd"]), refine=3)
+    assert rel_inf(buf.site_potential_boundary.cpu().numpy(), pb_o) <= TOL
+    pc = buf.site_potential_charge.cpu().numpy()
+    assert np.all(np.abs(pc - ref_c) <= TOL * np.abs(ref_c) + 1e-300)

@@ -16,9 +16,13 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
 traffic = {}
 fp64_pipe = None
-for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{rnd}_*.ncu-rep"))):
-    name = os.path.basename(rep)[len(f"prof_{rnd}_"):-len(".ncu-rep")]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+reps = {os.path.basename(r)[len(f"prof_{rnd}_"):-len(".ncu-rep")]: r for r in glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{rnd}_*.ncu-rep"))}
+raws = {os.path.basename(r)[len(f"prof_{rnd}_"):-len(".raw.csv")]: r for r in glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{rnd}_*.raw.csv"))}
+for name in sorted(set(reps) | set(raws)):
+    if name in raws and os.path.getsize(raws[name]) > 0:       # the raw page exported on the GPU box
+        out = open(raws[name]).read()
+    else:
+        out = subprocess.run(["ncu", "-i", reps[name], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     if len(rows) < 3:
         continue
@@ -62,7 +66,7 @@ if os.path.exists(lst):
 # bench.py keys
 tj = os.path.join(ROOT, "profiles", "traffic.json")
 old = json.load(open(tj)) if os.path.exists(tj) else {}
-m = {"spmv": "spmv_tile_kernel", "pairwise": "pairwise_cells_kernel", "rate_table": "rate_rows_kernel"}
+m = {"spmv": "spmv_tile_kernel", "spmv_solver_order": "spmv_tile_kernel", "pairwise": "pairwise_cells_kernel", "rate_table": "rate_rows_kernel", "pcg_solve": "pcg_persistent_kernel"}
 old["tiled_1M"] = {k: traffic[v] for k, v in m.items() if v in traffic}
 if fp64_pipe is not None:
     old["pairwise_fp64_pipe_pct"] = fp64_pipe
