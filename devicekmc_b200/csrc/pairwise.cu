@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(128) pw_cell_sort_kernel(const PwGrid *__restr
 // of its targets in (x, y, z) cell order and, inside a cell, the sources in ascending site index, two
 // per iteration into two accumulators per target (four independent FP64 chains per lane, every source
 // loaded once for two targets).  Same persistent tile scheduling and per-SM quota as pairwise_kernel.
-__global__ void __launch_bounds__(kPwMaxThreads, 3) pairwise_cells_kernel(
+template <int MINB>
+__global__ void __launch_bounds__(kPwMaxThreads, MINB) pairwise_cells_kernel(
     int row_begin, int row_end, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
     const PwGrid *__restrict__ gp, const int *__restrict__ cell_start, const ChargedSite *__restrict__ src,
     const int *__restrict__ src_idx, const double *__restrict__ sigma_ptr, const double *__restrict__ k_ptr,
@@ -574,6 +575,16 @@ static unsigned pw_linger_ns() {
     return v;
 }
 
+// Beside the CG the cell-list kernel runs in its 64-register build (launch bound 4 CTAs of 256 threads; ~400 bytes
+// of spills): at a share of 3 x 128 threads per SM it then holds 24.5 k instead of 30.7 k registers, which leaves the
+// persistent PCG 4 CTAs per SM instead of 3.  Measured at 1 M sites: the sum 26.5 -> 27.8 ms, the CG beside it
+// 35.3 -> 31.5 ms, the step 39.0 -> 35.0 ms (25.6 -> 28.6 KMC steps/s).  Alone the 80-register build is used.
+// DKMC_PW_LEAN=0: the 80-register build everywhere.
+static bool pw_lean() {
+    static const bool on = [] { const char *e = getenv("DKMC_PW_LEAN"); return e ? atoi(e) != 0 : true; }();
+    return on;
+}
+
 static bool pw_gate_enabled() {
     static const bool on = [] { const char *e = getenv("DKMC_PW_GATE"); return e ? atoi(e) != 0 : false; }();
     return on;
@@ -656,7 +667,7 @@ static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm
         const int which = cells ? 0 : (pbc ? 1 : 2);
         if (!regs[which]) {
             cudaFuncAttributes fa;
-            cudaError_t e = cells ? cudaFuncGetAttributes(&fa, pairwise_cells_kernel)
+            cudaError_t e = cells ? (pw_lean() ? cudaFuncGetAttributes(&fa, pairwise_cells_kernel<4>) : cudaFuncGetAttributes(&fa, pairwise_cells_kernel<3>))
                                   : (pbc ? cudaFuncGetAttributes(&fa, pairwise_kernel<true>) : cudaFuncGetAttributes(&fa, pairwise_kernel<false>));
             regs[which] = e == cudaSuccess ? fa.numRegs : 96;
         }
@@ -678,9 +689,15 @@ static int pairwise_launch(dkmc_ctx *ctx, cudaStream_t stream, int blocks_per_sm
         // and the two streams then ran one after the other (67 ms instead of 45 ms).  Asking for 16 KB of
         // (unused) dynamic shared memory, like the all-pairs kernel's staging tile, makes the split stick.
         static const int pad_smem = [] { const char *e = getenv("DKMC_PW_PAD_SMEM"); return e ? atoi(e) : 16384; }();
-        DKMC_LAUNCH_ON(ctx, stream, pairwise_cells_kernel, grid, threads, pad_smem, row_begin, row_end, d_x, d_y, d_z, cells->grid,
-                       cells->cell_start, cells->src, cells->src_idx, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm,
-                       pw_linger_ns(), cells->pair_counter, accumulate, ctx->pw_far_field, d_out);
+        if (pw_lean() && shared_sms) {
+            DKMC_LAUNCH_ON(ctx, stream, pairwise_cells_kernel<4>, grid, threads, pad_smem, row_begin, row_end, d_x, d_y, d_z, cells->grid,
+                           cells->cell_start, cells->src, cells->src_idx, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm,
+                           pw_linger_ns(), cells->pair_counter, accumulate, ctx->pw_far_field, d_out);
+        } else {
+            DKMC_LAUNCH_ON(ctx, stream, pairwise_cells_kernel<3>, grid, threads, pad_smem, row_begin, row_end, d_x, d_y, d_z, cells->grid,
+                           cells->cell_start, cells->src, cells->src_idx, d_sigma, d_k, tile_counter, sm_count, blocks_per_sm,
+                           pw_linger_ns(), cells->pair_counter, accumulate, ctx->pw_far_field, d_out);
+        }
         if (shared_sms && pw_gate_enabled()) DKMC_LAUNCH(ctx, pw_gate_kernel, 1, 1, 0, sm_count + 256, grid);
         return DKMC_OK;
     }
