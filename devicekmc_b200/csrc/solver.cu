@@ -969,18 +969,18 @@ constexpr int kPcgProfLen = 8 + 2 * 2048;   // phase sums of CTA 0 | per CTA: Sp
 // launch bounds of 6, 5, 4 CTAs per SM (40, 48, 64 registers).
 typedef void (*PcgKernel)(const PcgArgs);
 // family 0: Chronopoulos-Gear (two synchronisations per iteration), family 1: pipelined (one)
-static const PcgKernel kPcgKernels[2][3] = {
-    {pcg_persistent_kernel<6, false>, pcg_persistent_kernel<5, false>, pcg_persistent_kernel<4, false>},
-    {pcg_pipelined_kernel<6, false>, pcg_pipelined_kernel<5, false>, pcg_pipelined_kernel<4, false>}};
-static const PcgKernel kPcgKernelsProf[2][3] = {
-    {pcg_persistent_kernel<6, true>, pcg_persistent_kernel<5, true>, pcg_persistent_kernel<4, true>},
-    {pcg_pipelined_kernel<6, true>, pcg_pipelined_kernel<5, true>, pcg_pipelined_kernel<4, true>}};
+static const PcgKernel kPcgKernels[2][4] = {
+    {pcg_persistent_kernel<6, false>, pcg_persistent_kernel<5, false>, pcg_persistent_kernel<4, false>, pcg_persistent_kernel<8, false>},
+    {pcg_pipelined_kernel<6, false>, pcg_pipelined_kernel<5, false>, pcg_pipelined_kernel<4, false>, pcg_pipelined_kernel<8, false>}};
+static const PcgKernel kPcgKernelsProf[2][4] = {
+    {pcg_persistent_kernel<6, true>, pcg_persistent_kernel<5, true>, pcg_persistent_kernel<4, true>, pcg_persistent_kernel<8, true>},
+    {pcg_pipelined_kernel<6, true>, pcg_pipelined_kernel<5, true>, pcg_pipelined_kernel<4, true>, pcg_pipelined_kernel<8, true>}};
 
 static int pcg_ctas_per_sm(dkmc_ctx *ctx, int family, int *variant) {
-    static int occ_all[2][3] = {{0, 0, 0}, {0, 0, 0}}, regs_all[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    static int occ_all[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, regs_all[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     int *occ = occ_all[family], *regs = regs_all[family];
     if (!occ[0]) {
-        for (int v = 0; v < 3; ++v) {
+        for (int v = 0; v < 4; ++v) {
             cudaFuncAttributes fa;
             regs[v] = cudaFuncGetAttributes(&fa, kPcgKernels[family][v]) == cudaSuccess ? fa.numRegs : 40 + 8 * v;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], kPcgKernels[family][v], kSpmvThreads, 0) != cudaSuccess || occ[v] < 1) occ[v] = 1;
@@ -995,7 +995,7 @@ static int pcg_ctas_per_sm(dkmc_ctx *ctx, int family, int *variant) {
     const bool overlapped = ctx->pw_pending.active && cudaEventQuery(ctx->ev_pw1) == cudaErrorNotReady;
     int v = 0;
     const int cv = cfg[overlapped ? 3 : 1];
-    if (cv >= 0 && cv < 3) v = cv;
+    if (cv >= 0 && cv < 4) v = cv;
     int cps = occ[v];
     if (overlapped) {
         // registers and threads the pairwise CTAs hold on every SM (allocation granularity: 8 registers per thread)
