@@ -124,6 +124,17 @@ class SlabSim:
         self.chunk = chunk_padded(N, world)
         self._pc_full = torch.zeros(self.chunk * world, dtype=torch.float64, device="cuda")
         self.buf.site_potential_charge = self._pc_full[:N]
+        # the other per-step arrays likewise (slab-wise host <-> device syncs + one all-gather, sync_slab_*)
+        self._full = {"site_potential_charge": self._pc_full}
+        if world > 1:
+            for name in self.buf._SYNCED:
+                if name in self._full:
+                    continue
+                old = getattr(self.buf, name)
+                full = torch.zeros(self.chunk * world, dtype=old.dtype, device="cuda")
+                full[:N].copy_(old)
+                self._full[name] = full
+                setattr(self.buf, name, full[:N])
         self.i0 = min(N, rank * self.chunk)
         self.i1 = min(N, (rank + 1) * self.chunk)
         self._rows_b = np.array([min(N, r * self.chunk) for r in range(world)], np.int32)
@@ -152,6 +163,34 @@ class SlabSim:
                 # partition saves at this size, so every rank solves the whole system instead
                 self.dcg.close()
                 self.dcg = None
+
+    def sync_slab_HostToGPU(self):
+        """gpu_buffers.cpp:10-37 for a host that is partitioned like the device: every rank uploads only the rows of
+        its slab (N / world sites instead of all N through the one host's PCIe lanes); one all-gather per array over
+        NVLink completes the replicated device arrays the event loop needs."""
+        if self.world == 1:
+            return self.buf.sync_HostToGPU(self.dev)
+        a, b = self.i0, self.i1
+        for name in self.buf._SYNCED:
+            full = self._full[name]
+            if b > a:
+                full[a:b].copy_(self.buf._pinned(self.dev, name)[a:b], non_blocking=True)
+            mine = full[self.rank * self.chunk:(self.rank + 1) * self.chunk].clone()
+            self.dist.all_gather_into_tensor(full, mine)
+        self.buf.T_bg.fill_(self.dev.T_bg)
+
+    def sync_slab_GPUToHost(self):
+        """gpu_buffers.cpp:39-55, slab-wise: the host arrays of this rank are current in its slab's rows"""
+        if self.world == 1:
+            return self.buf.sync_GPUToHost(self.dev)
+        a, b = self.i0, self.i1
+        if b > a:
+            for name in self.buf._SYNCED:
+                self.buf._pinned(self.dev, name)[a:b].copy_(self._full[name][a:b], non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+
+    def slab_bytes(self) -> int:
+        return (self.i1 - self.i0) * (4 + 4 + 8 + 8 + 8)
 
     def step(self, Vd: float, record_events: int = 0):
         import devicekmc_b200 as D
@@ -317,9 +356,9 @@ def bench_multi_gpu(args, metric: str, unit: str):
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     e0.record()
     for _ in range(args.steps):
-        s.buf.sync_HostToGPU(s.dev)
+        s.sync_slab_HostToGPU()
         s.step(args.vd)
-        s.buf.sync_GPUToHost(s.dev)
+        s.sync_slab_GPUToHost()
     e1.record(); e1.synchronize()
     ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
@@ -355,8 +394,10 @@ def bench_multi_gpu(args, metric: str, unit: str):
                                else "slab-partitioned, NCCL" if s.dcg is not None else "replicated"),
                         "pairwise_share_ctas_per_sm": stats[-1].get("pairwise_share")},
                 "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": args.steps / (ms2.item() * 1e-3), "unit": unit, "h2d_bytes_per_step": s.buf.h2d_bytes(),
-                        "d2h_bytes_per_step": s.buf.d2h_bytes()},
+                "e2e": {"value": args.steps / (ms2.item() * 1e-3), "unit": unit, "h2d_bytes_per_step": s.slab_bytes() * world,
+                        "d2h_bytes_per_step": s.slab_bytes() * world,
+                        "note": "host partitioned like the device: every rank moves its slab's rows (h2d/d2h bytes are the "
+                                "job's totals) and one all-gather per array over NVLink completes the replicated device arrays"},
                 "stage_ms": {"cg_solve": med("solve_ms"), "pairwise_concurrent": med("pairwise_ms"),
                              "assemble": med("assemble_ms"), "rate_table": med("rate_ms"),
                              "event_loop": med("loop_ms"),
