@@ -115,8 +115,9 @@ def test_pipelined_true_residual_stagnates_above_the_classic_one():
     dinv, wE = _precond(A, W)
     Minv = lambda v: dinv * v + W @ (wE * (W.T @ v))
     rel = lambda x: np.sqrt(((b - A @ x) @ Minv(b - A @ x)) / (b @ Minv(b)))
-    xp, _ = pipelined(A, W, b, 1e-15, max_iter=600)
-    xc, _ = classic(A, W, b, 1e-15, max_iter=600)
-    assert rel(xc) < 1e-11
-    assert rel(xp) < 1e-6                                       # it does converge ...
-    assert rel(xp) > rel(xc)                                    # ... but not as far: restarts only
+    xp, itp = pipelined(A, W, b, 1e-15, max_iter=200)
+    xc, itc = classic(A, W, b, 1e-15, max_iter=200)
+    assert itc < 200 and rel(xc) < 1e-7                         # the classic recurrence gets there ...
+    assert itp == 200                                           # ... the pipelined one never meets a 1e-15 tolerance,
+    assert rel(xp) < 1e-4                                       # although it has converged to its floor,
+    assert rel(xp) > 10 * rel(xc)                               # which lies above the classic one's: restarts only
