@@ -17,6 +17,7 @@
 #include "gpu_solvers.h"
 
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <vector>
 
@@ -73,6 +74,40 @@ void copytoConstMemory(std::vector<double> E_gen, std::vector<double> E_rec, std
                       "copytoConstMemory");
 }
 
+// The reference's site order puts all lattice atoms before all interstitials (reorder_boundary.py:113-124): the rows
+// of K are then not spatially sorted.  Give the solver an internal row order — interior rows x-major by 3.6 A grid
+// cell, ties in the caller's order — unless the input already has it (dkmc_solver_set_order; every public array keeps
+// the caller's order).  Same rule as the Python mirror (devicekmc_b200/structures.py: cell_order).
+static void register_solver_order(GPUBuffers &gpubuf, const dkmc_sparsity &sp, int n_contact) {
+    const int N = gpubuf.N_, m = sp.m;
+    if (m <= 0 || m != N - 2 * n_contact) return;
+    std::vector<double> x(N), y(N), z(N);
+    if (cudaMemcpy(x.data(), gpubuf.site_x, sizeof(double) * N, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(y.data(), gpubuf.site_y, sizeof(double) * N, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(z.data(), gpubuf.site_z, sizeof(double) * N, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    double x0 = x[0];
+    for (int i = 1; i < N; ++i) x0 = x[i] < x0 ? x[i] : x0;
+    const double edge = 3.6;
+    std::vector<long long> key(m);
+    for (int r = 0; r < m; ++r) {
+        const int i = n_contact + r;
+        const long long cx = (long long)std::floor((x[i] - x0) / edge), cy = (long long)std::floor(y[i] / edge),
+                        cz = (long long)std::floor(z[i] / edge);
+        key[r] = ((cx + (1ll << 19)) << 42) | ((cy + (1ll << 20)) << 21) | (cz + (1ll << 20));
+    }
+    std::vector<int> order(m);
+    for (int r = 0; r < m; ++r) order[r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    bool identity = true;
+    for (int r = 0; r < m && identity; ++r) identity = order[r] == r;
+    if (identity) return;
+    int *d_order = nullptr;
+    if (cudaMalloc(&d_order, sizeof(int) * (size_t)m) != cudaSuccess) return;
+    cudaMemcpy(d_order, order.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice);
+    report(dkmc_solver_set_order(ctx(), &sp, d_order), "initialize_sparsity (solver row order)");
+    cudaFree(d_order);
+}
+
 // gpu_solvers.h:43 — the CSR index buffers become members of gpubuf, as in the reference
 void initialize_sparsity(GPUBuffers &gpubuf, int pbc, const double nn_dist, int num_atoms_contact) {
     (void)pbc; (void)nn_dist;  // the structure follows from gpubuf.neigh_idx (same cutoff, Device.cpp:98-136)
@@ -86,6 +121,7 @@ void initialize_sparsity(GPUBuffers &gpubuf, int pbc, const double nn_dist, int 
     gpubuf.contact_left_nnz = sp.left_nnz;
     gpubuf.contact_right_row_ptr = sp.d_right_row_ptr; gpubuf.contact_right_col_indices = sp.d_right_col;
     gpubuf.contact_right_nnz = sp.right_nnz;
+    register_solver_order(gpubuf, sp, num_atoms_contact);
 }
 
 // gpu_solvers.h:127-130
