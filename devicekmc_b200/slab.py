@@ -235,10 +235,7 @@ class SlabSim:
                 want = min(3, want + 1)
             elif pw_ms.value < 0.5 * info.solve_ms:
                 want = max(1 if self.world > 1 else 2, want - 1)
-            if self.world > 1:      # every rank the same share: the slowest rank sets the pace
-                tw = self.torch.tensor([want], dtype=self.torch.int32, device="cuda")
-                self.dist.all_reduce(tw, op=self.dist.ReduceOp.MAX)
-                want = int(tw.item())
+            # (every rank decides for itself: the ranks' grids need not agree, and a KMC step stays free of NCCL calls)
             if want != self._share[0]:
                 self._share[0] = want
                 check(lib.dkmc_ctx_set_pairwise_share(dev.ctx.h, want, self._share[1]))
