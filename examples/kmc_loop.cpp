@@ -15,6 +15,8 @@
 // (devicekmc_b200/shim/).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -114,6 +116,31 @@ int main(int argc, char **argv) {
     CK(dkmc_set_layer_energies(ctx, 5, E_gen, E_rec, E_Vdiff, E_Odiff));
     dkmc_sparsity sp;
     CK(dkmc_initialize_sparsity(ctx, N, nn, d_neigh, n_contact, n_contact, &sp));
+    {
+        // the file is in the reference's site order (lattice atoms, then interstitials): give the solver an internal
+        // row order — interior rows x-major by 3.6 A grid cell — unless the rows already have it; every array of this
+        // program keeps the file's order (dkmc_solver_set_order)
+        const double x0 = *std::min_element(x.begin(), x.end()), edge = 3.6;
+        std::vector<long long> key(sp.m);
+        std::vector<int> order(sp.m);
+        for (int r = 0; r < sp.m; ++r) {
+            const int i = n_contact + r;
+            const long long cx = (long long)std::floor((x[i] - x0) / edge), cy = (long long)std::floor(y[i] / edge),
+                            cz = (long long)std::floor(z[i] / edge);
+            key[r] = ((cx + (1ll << 19)) << 42) | ((cy + (1ll << 20)) << 21) | (cz + (1ll << 20));
+            order[r] = r;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+        bool sorted_already = true;
+        for (int r = 0; r < sp.m && sorted_already; ++r) sorted_already = order[r] == r;
+        if (!sorted_already) {
+            int *d_order = to_device(order);
+            if (!d_order) { fprintf(stderr, "cudaMalloc failed\n"); return 1; }
+            CK(dkmc_solver_set_order(ctx, &sp, d_order));
+            cudaFree(d_order);
+            printf("solver row order: x-major grid cells (input not spatially sorted)\n");
+        }
+    }
 
     // ---- the KMC loop
     std::mt19937 rng(1);                                                       // rnd_seed_kmc, structure_input.h:8

@@ -177,3 +177,28 @@ def test_28k_tile_matches_the_reference_build(O, torch):
     assert rel_inf(buf.site_potential_boundary.cpu().numpy(), pb_o) <= TOL
     pc = buf.site_potential_charge.cpu().numpy()
     assert np.all(np.abs(pc - ref_c) <= TOL * np.abs(ref_c) + 1e-300)
+
+
+def test_solver_order_rejects_what_is_not_a_permutation_and_invalidate_rebuilds(dev75, torch):
+    """dkmc_solver_set_order checks its argument; dkmc_ctx_invalidate drops the address-keyed caches and the next
+    solve rebuilds them (same solution)"""
+    from devicekmc_b200 import _capi
+    from devicekmc_b200._capi import check
+    p, dev, buf, nc, Vd = dev75["p"], dev75["dev"], dev75["buf"], dev75["nc"], dev75["Vd"]
+    sp = buf.sparsity(nc, nc)
+    lib = dev.ctx.lib
+    bad = buf._order_tensor.clone()
+    bad[1] = bad[0]                                           # a repeated row
+    assert lib.dkmc_solver_set_order(dev.ctx.h, C.byref(sp), bad.data_ptr()) == _capi.DKMC_ERR_ARG
+    bad[1] = sp.m                                             # out of range
+    assert lib.dkmc_solver_set_order(dev.ctx.h, C.byref(sp), bad.data_ptr()) == _capi.DKMC_ERR_ARG
+    # a rejected order leaves the solver in the caller's order: still the same solution
+    out = dev.updatePotential(buf, p, Vd, n_contact=nc)
+    assert out["cg_converged"]
+    ref = buf.site_potential_boundary.clone()
+    check(lib.dkmc_solver_set_order(dev.ctx.h, C.byref(sp), buf._order_tensor.data_ptr()))
+    check(lib.dkmc_ctx_invalidate(dev.ctx.h))
+    buf.site_potential_boundary.zero_()
+    out = dev.updatePotential(buf, p, Vd, n_contact=nc)
+    assert out["cg_converged"]
+    assert float((buf.site_potential_boundary - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
