@@ -22,6 +22,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at the VERSION level) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "kmc_steps_per_sec"
 UNIT = "steps/s"
