@@ -725,10 +725,18 @@ static int run_pcg_persistent_single(dkmc_ctx *ctx, int m, int nnz, const int *d
 static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const int *d_col, const double *d_val,
                    const double *d_b, double *d_x, const CgWork &w, double tol, int max_iter, int check_every,
                    int *iters_out, int *converged, double *bb_out) {
-    if (use_persistent_pcg(ctx))
-        return run_pcg_persistent_single(ctx, m, nnz, d_row_ptr, d_col, d_val, d_b, d_x, w, tol, max_iter, iters_out, converged,
-                                         bb_out);
-    // legacy path (DKMC_LEGACY_CG=1): three launches per iteration, the host polls a flag every `check_every`
+    int persistent_its = 0;
+    if (use_persistent_pcg(ctx)) {
+        int rcp = run_pcg_persistent_single(ctx, m, nnz, d_row_ptr, d_col, d_val, d_b, d_x, w, tol, max_iter, iters_out, converged,
+                                            bb_out);
+        if (rcp != DKMC_OK || *converged || *iters_out < max_iter) return rcp;
+        // max_iter reached without convergence: on spectra with extreme outliers (floating metal islands)
+        // the rearranged scalars of the one-reduction recurrence can stagnate where the textbook recurrence still
+        // converges — carry on from the current x with the per-operation path below
+        persistent_its = *iters_out;
+    }
+    // per-operation path (DKMC_LEGACY_CG=1, or the fall-back above): three launches per iteration, the host polls a
+    // flag every `check_every`
     const int vg = vec_grid(ctx, m);
     // r = b - A x, then z/p/rz/bb
     int rc0;
@@ -764,7 +772,7 @@ static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const in
         DKMC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (h.done || launched >= max_iter) break;
     }
-    *iters_out = h.iters;
+    *iters_out = h.iters + persistent_its;
     *converged = (h.rz <= h.stop) ? 1 : 0;
     if (bb_out) *bb_out = h.bb;
     return DKMC_OK;
