@@ -976,7 +976,9 @@ constexpr int kPcgProfLen = 8 + 2 * 2048;   // phase sums of CTA 0 | per CTA: Sp
 // Three instantiations trade registers per thread (loads in flight) against CTAs per SM: *variant = 0, 1, 2 for
 // launch bounds of 6, 5, 4 CTAs per SM (40, 48, 64 registers).
 typedef void (*PcgKernel)(const PcgArgs);
-// family 0: Chronopoulos-Gear (two synchronisations per iteration), family 1: pipelined (one)
+// family 0: Chronopoulos-Gear (two synchronisations per iteration), family 1: pipelined (one).  Variants 0, 1, 2 =
+// launch bounds of 6, 5, 4 CTAs per SM (40, 48, 64 registers); variant 3 = 8 CTAs (32 registers), an experiment that
+// gained nothing beside the pairwise kernel (5 instead of 4 resident CTAs, more spills) and is never chosen by default.
 static const PcgKernel kPcgKernels[2][4] = {
     {pcg_persistent_kernel<6, false>, pcg_persistent_kernel<5, false>, pcg_persistent_kernel<4, false>, pcg_persistent_kernel<8, false>},
     {pcg_pipelined_kernel<6, false>, pcg_pipelined_kernel<5, false>, pcg_pipelined_kernel<4, false>, pcg_pipelined_kernel<8, false>}};
