@@ -730,9 +730,9 @@ static int run_pcg(dkmc_ctx *ctx, int m, int nnz, const int *d_row_ptr, const in
         int rcp = run_pcg_persistent_single(ctx, m, nnz, d_row_ptr, d_col, d_val, d_b, d_x, w, tol, max_iter, iters_out, converged,
                                             bb_out);
         if (rcp != DKMC_OK || *converged || *iters_out < max_iter) return rcp;
-        // max_iter reached without convergence: on spectra with extreme outliers (floating metal islands)
-        // the rearranged scalars of the one-reduction recurrence can stagnate where the textbook recurrence still
-        // converges — carry on from the current x with the per-operation path below
+        // max_iter reached without convergence (seen once: floating metal islands): do not give up
+        // before the textbook two-reduction recurrence of the per-operation path below has had its turn, from the
+        // current x
         persistent_its = *iters_out;
     }
     // per-operation path (DKMC_LEGACY_CG=1, or the fall-back above): three launches per iteration, the host polls a

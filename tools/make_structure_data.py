@@ -7,7 +7,7 @@ interstitials, reorder_boundary.py:113-124); n_contact = num_atoms_contact of th
 contact size of the reference's CPU branch (potential_solver.cpp:271,294) — the semantics the oracle follows.  Its
 GPU branch passes num_atoms_first_layer instead (potential_solver.cpp:240-241; kept as n_first_layer): on the
 crossbar that leaves two of the four electrode lines floating (5 761 and 7 920 metal sites tied by high_G, held
-only through low_G), a near-singular system that no Jacobi-type CG solves in 20 000 iterations."""
+only through low_G); on the 2 x 2 tile with that contact size the GPU solve used up 20 000 iterations."""
 import os
 import sys
 
